@@ -1,0 +1,130 @@
+/*
+ * plsb200 -- C ABI of the B200-native resampling engine for plspy (McIntosh-Lab/plspy).
+ *
+ * This is the drop-in boundary for ONE path of the reference: the permutation test, the bootstrap
+ * test and the split-half loops of `plspy.core` (reference seam:
+ * plspy/core/bootstrap_permutation.py:53-63,139-263 `ResampleTest._create` and
+ * plspy/core/split_half_resampling.py:23,404).  The reference is pure Python/numpy, so the binding a
+ * maintainer adds is a ctypes stub; every entry point takes plain pointers and
+ * sizes only.
+ *
+ * Conventions
+ *  - all matrices are float64, row-major, resident in DEVICE memory unless the name ends in `_host`;
+ *  - index matrices are int32, row-major, one resample per row (values in [0, N));
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); all calls are asynchronous
+ *    with respect to the host except where stated;
+ *  - every function returns 0 on success, a negative PLSB200_E* code otherwise;
+ *    plsb200_last_error() returns a thread-local message for the last failure;
+ *  - the library allocates nothing that outlives a call: workspaces are caller-provided and sized by
+ *    the matching *_workspace() query (bytes).
+ *  - the caller owns all buffers (reference ownership: fresh numpy arrays owned by the result object,
+ *    bootstrap_permutation.py:496-532).
+ *
+ * Notation: N rows of X (subjects x conditions), p voxels, K columns of the
+ * coefficient matrix (latent variables / contrasts), R resamples in the batch.
+ *   E  (N x K)  = Lop^T . U   : design-side weights pulled back to row space, constant per analysis
+ *   C_r (N x K) = S_r^T . E   : C_r[idx_r[i], :] += E[i, :]          (scatter of E by one index vector)
+ *   VS_r (p x K) = X^T . C_r  : the resampled, projected cross-block matrix `permuted.T @ U`
+ *                               (bootstrap_permutation.py:404, :620)
+ */
+#ifndef PLSB200_H
+#define PLSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLSB200_ABI_VERSION 1
+
+#define PLSB200_OK 0
+#define PLSB200_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */
+#define PLSB200_ECUDA (-2)    /* CUDA runtime / launch error                   */
+#define PLSB200_EWORKSPACE (-3) /* workspace too small                          */
+#define PLSB200_EUNSUPPORTED (-4) /* shape outside what the kernels are built for */
+
+int plsb200_abi_version(void);
+const char* plsb200_last_error(void);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+int64_t plsb200_launch_count(void);
+
+/* ---- K1: Gram matrix G = X . X^T (N x N), FP64 DMMA, split over voxel chunks, deterministic --------
+ * Replaces the N x p work that every resample redoes in the reference (row gather + means + projection,
+ * resample.py:79,153 + class_functions.py:7-95 + bootstrap_permutation.py:404): once G is known every
+ * per-resample quantity except std_errs lives in N-space.
+ * X: N x p with leading dimension ldx (elements).  G: N x N dense, both triangles written.        */
+size_t plsb200_gram_f64_workspace(int N, int64_t p);
+int plsb200_gram_f64(const double* X, int N, int64_t p, int64_t ldx, double* G,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- latent projection XL = X . V (N x K); replaces class_functions._compute_X_latents
+ * (class_functions.py:165-182) as used for U_hat (bootstrap_permutation.py:617).
+ * V: p x K row-major.                                                                              */
+size_t plsb200_xv_f64_workspace(int N, int64_t p, int K);
+int plsb200_xv_f64(const double* X, int N, int64_t p, int64_t ldx, const double* V, int K,
+                   double* XL, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2/K6: N-space pass over a batch of resamples ------------------------------------------------
+ * For each resample r (index vector idx[r, 0..N)):
+ *     H_r  = G . C_r                                   (N x K)
+ *     d2[r, k] = C_r[:, k]^T . H_r[:, k] = ||VS_r[:, k]||^2     (squared singular-value estimate,
+ *                                                       bootstrap_permutation.py:405 / :432)
+ *     if Lmat != NULL:  T[r] = Lmat (Kt x N) . H_r . diag(1/sqrt(d2[r]))   (Kt x K)
+ *                       = cellmeans(X @ normalize(VS_r)), the bootstrap `Tdistrib`
+ *                       (bootstrap_permutation.py:633-634, :665-666); zero where d2 == 0.
+ * Gather formulation, no atomics, deterministic.  d2: R x K.  T: R x Kt x K (may be NULL).          */
+int plsb200_nspace_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
+                       const double* Lmat, int Kt, double* d2, double* T, void* stream);
+
+/* ---- permutation counters -------------------------------------------------------------------------
+ * s_hat = sqrt(d2) (set to 0 where |s_hat| < thresh when thresh > 0: bootstrap_permutation.py:436),
+ * counts[k]     += (s_hat[r,k] >= s_ref[k])                              (:427/:433/:437)
+ * counts[K + k] += (sum_{j>=k} s_hat[r,j]^2 >= totcov_ref[k])            (stepdown, :446-451)
+ * `mb_total` (R) non-NULL applies the multiblock rescale s_hat <- sqrt(s_hat^4 / sum s_hat^4 * mb_total[r])
+ * first (:419-424).  counts: int64[2K], ACCUMULATED into (caller zeroes).  s_hat: R x K out.         */
+int plsb200_perm_count_f64(const double* d2, int R, int K, const double* s_ref, const double* totcov_ref,
+                           double thresh, const double* mb_total, int64_t* counts, double* s_hat,
+                           void* stream);
+
+/* ---- U_hat_r = Lop (Ku x N) . XL[idx_r, :] (N x K)  -> Uhat: R x Ku x K   (bootstrap_permutation.py:617) */
+int plsb200_uhat_f64(const double* XL, int N, int K, const double* Lop, int Ku, const int32_t* idx, int R,
+                     double* Uhat, void* stream);
+
+/* ---- K4: bootstrap salience moments ---------------------------------------------------------------
+ * The batched GEMM  VS[v, (r,k)] = sum_i X[i, v] . C_r[i, k]  over all R resamples, with
+ * sum_r (VS - pivot) and sum_r (VS - pivot)^2 accumulated in registers; nothing of size p x K x R is
+ * written (the reference materialises right_sv_sampled, bootstrap_permutation.py:497,626,695).
+ *
+ * Step 1 packs the coefficients C_r = scatter(E, idx_r) into the DMMA B-fragment order the kernel
+ * streams through shared memory (`coef`, size from plsb200_boot_coef_bytes).
+ * Step 2 runs the GEMM+moment kernel.  pivot (p x K) may be NULL (= 0).  sum, sumsq: p x K, overwritten.
+ * Supported shapes: K <= 24 per call (split wider problems by column), N <= 320 * 4.               */
+size_t plsb200_boot_coef_bytes(int N, int K, int R);
+int plsb200_boot_coef_pack_f64(const double* E, int N, int K, const int32_t* idx, int R, double* coef,
+                               void* stream);
+size_t plsb200_boot_moments_f64_workspace(int N, int64_t p, int K, int R);
+int plsb200_boot_moments_f64(const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                             int R, const double* pivot, double* sum, double* sumsq,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- std_errs / boot_ratios from the moments (bootstrap_permutation.py:695-703) --------------------
+ * mean = pivot + sum/R ; std_errs = sqrt(max(sumsq/R - (sum/R)^2, 0)) (population std, ddof = 0);
+ * boot_ratios = numer / std_errs  with numer = V*s (no contrast) or V (contrast), p x K.            */
+int plsb200_boot_finalize_f64(const double* sum, const double* sumsq, int64_t p, int K, int64_t R_total,
+                              const double* numer, double* std_errs, double* boot_ratios, void* stream);
+
+/* ---- population std over the first axis of a (R x M) matrix -> M values (np.std(..., axis=0),
+ * bootstrap_permutation.py:715,723,732)                                                             */
+int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* stream);
+
+/* ---- explicit saliences for a small batch: VS[r] = X^T . C_r  (R x p x K), for callers that ask for
+ * boot_debug_dict["right_sv_sampled"] on problems small enough to hold it.                          */
+int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
+                         const int32_t* idx, int R, double* VS, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSB200_H */

@@ -1,0 +1,508 @@
+// K4: bootstrap salience moments -- the dominant kernel of the path (>99% of the algorithmic flops).
+//
+// Reference (bootstrap_permutation.py:557-626, 695): per bootstrap, gather N rows of X, rebuild the
+// K x p cross-block matrix, VS_hat = permuted.T @ U (p x K) is stored in right_sv_sampled[B, p, K] and
+// std_errs = np.std(right_sv_sampled, axis=0) at the end.  Here VS_r = X^T . C_r with
+// C_r = scatter(E, idx_r) (N x K), so all resamples form ONE skinny GEMM
+//       VS[v, (r,k)] = sum_i X[i, v] . C[i, (r,k)]          M = p, N = R*K, K-dim = N rows
+// whose output is reduced over r on the fly: sum_r (VS - pivot), sum_r (VS - pivot)^2.
+//
+// Mapping onto the FP64 tensor path (DMMA.8x8x4, 37 TFLOP/s measured on B200):
+//   * M (8 per MMA) = voxels.  A warp owns 8 voxels and keeps ALL its A-fragments -- X[0..N, v0..v0+8) --
+//     in registers for the whole kernel (N/4 doubles per thread: 75 for N = 300).  X is read from HBM
+//     exactly once per CTA row-tile and never staged in shared memory.
+//   * N (8 per MMA) = flattened (resample, k) columns.  The coefficient tensor is pre-packed in the
+//     exact B-fragment order (lane-major 256-byte blocks), so the TMA engine streams it into shared
+//     memory with plain 1-D bulk copies (cp.async.bulk / UBLKCP, mbarrier completion) and every
+//     fragment load is one conflict-free LDS.64.  It is shared by the 8 warps of the CTA.
+//   * A "period" is 8*NBLK columns = nb whole resamples (K=12 -> 24 columns = 2 resamples, no padding).
+//     Within a period the NBLK accumulator chains are independent, which hides the DMMA latency.
+//   * After N/4 chained MMAs a D fragment holds VS - pivot (the chain starts from -pivot) for 8 voxels
+//     x 8 columns; it is folded into per-thread running sums and discarded.  Column -> k is fixed per
+//     thread for the whole kernel because the period is a multiple of K.
+// Shared memory: nstage x (N/4 * NBLK * 256 B) ring (57.6 KB per stage at N=300, K=12 -> 3 stages).
+#include "common.cuh"
+
+namespace plsb {
+
+constexpr int BM_WARPS = 8;          // consumer warps per CTA
+constexpr int BM_THREADS = BM_WARPS * 32;
+constexpr int BM_VOX = BM_WARPS * 8; // voxels per CTA
+
+struct BootPlan {
+    int Kp;        // padded K (divides 8*nblk)
+    int nblk;      // 8-column blocks per period
+    int nb;        // resamples per period
+    int nks;       // k-steps of 4 rows (multiple of 4)
+    int maxks;     // template bucket
+    int nper;      // periods
+    int nstage;
+    size_t stage_doubles;
+    size_t smem_bytes;
+    int nsplit;        // splits of the period range (grid.y)
+    int per_per_split;
+};
+
+static bool boot_plan(int N, int K, int R, int64_t p, BootPlan& b) {
+    if (K < 1 || K > 24 || N < 1 || R < 1) return false;
+    // smallest padded K that divides a 24-, 16- or 8-column period; prefer wider periods (more ILP)
+    int best_kp = 0, best_blk = 0;
+    for (int blk = 3; blk >= 1; --blk) {
+        const int cols = 8 * blk;
+        for (int kp = K; kp <= cols; ++kp) {
+            if (cols % kp == 0) {
+                if (best_kp == 0 || kp < best_kp) { best_kp = kp; best_blk = blk; }
+                break;
+            }
+        }
+    }
+    if (!best_kp) return false;
+    b.Kp = best_kp; b.nblk = best_blk; b.nb = 8 * best_blk / best_kp;
+    b.nks = (int)cdiv(N, 16) * 4;
+    if (b.nks <= 20) b.maxks = 20; else if (b.nks <= 40) b.maxks = 40; else if (b.nks <= 60) b.maxks = 60;
+    else if (b.nks <= 80) b.maxks = 80; else return false;
+    b.nper = (int)cdiv(R, b.nb);
+    b.stage_doubles = (size_t)b.nks * b.nblk * 32;
+    const size_t red = (size_t)BM_WARPS * 8 * b.Kp * 2 * sizeof(double);
+    const size_t avail = 227 * 1024 - red - 256;
+    int ns = (int)(avail / (b.stage_doubles * sizeof(double)));
+    if (ns > 4) ns = 4;
+    if (ns < 2) return false;
+    b.nstage = ns;
+    b.smem_bytes = ns * b.stage_doubles * sizeof(double) + red + 256;
+    // split the resample range so that tiles*nsplit fills whole waves of SMs
+    const int64_t tiles = cdiv(p > 0 ? p : 1, BM_VOX);
+    const int nsm = num_sms();
+    int best = 1; double best_cost = 1e30;
+    for (int n = 1; n <= 8; ++n) {
+        if (n > 1 && b.nper / n < 8) break;
+        const double waves = (double)tiles * n / nsm;
+        const double cost = ceil(waves) / waves + 0.004 * (n - 1);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = n; }
+    }
+    b.nsplit = best;
+    b.per_per_split = (int)cdiv(b.nper, best);
+    b.nsplit = (int)cdiv(b.nper, b.per_per_split);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// coefficient packing: C_r = scatter(E, idx_r) written in B-fragment order.
+// offset(per, s, jb, lane) = ((per*nks + s)*nblk + jb)*32 + lane,  lane = 4*n + q,
+// column-in-period c = (r % nb)*Kp + k -> jb = c/8, n = c%8 ; row i -> s = i/4, q = i%4.
+// One CTA per resample; thread i scans idx for sources of target row i in index order (deterministic).
+__global__ void __launch_bounds__(256) boot_coef_pack_kernel(const double* __restrict__ E, int N, int K,
+                                                            const int32_t* __restrict__ idx, int Kp, int nblk,
+                                                            int nb, int nks, double* __restrict__ coef) {
+    extern __shared__ __align__(16) double smp[];
+    double* Es = smp;                                   // [N][K]
+    int* ids = reinterpret_cast<int*>(Es + (size_t)N * K);
+    const int r = blockIdx.x;
+    const int32_t* my = idx + (size_t)r * N;
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) Es[i] = E[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = my[i];
+    __syncthreads();
+    const int per = r / nb, cbase = (r % nb) * Kp;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double acc[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) acc[k] = 0.0;
+        for (int src = 0; src < N; ++src) {
+            if (ids[src] == i) {
+#pragma unroll
+                for (int k = 0; k < 24; ++k)
+                    if (k < K) acc[k] += Es[src * K + k];
+            }
+        }
+        const int s = i >> 2, q = i & 3;
+#pragma unroll
+        for (int k = 0; k < 24; ++k) {
+            if (k < K) {
+                const int c = cbase + k;
+                coef[((size_t)(per * nks + s) * nblk + (c >> 3)) * 32 + 4 * (c & 7) + q] = acc[k];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int MAXKS, int NBLK>
+__global__ void __launch_bounds__(BM_THREADS, 1)
+boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
+                    const double* __restrict__ coef, int nks, int nper, int per_per_split, int nstage,
+                    int R, int Kp, int K, const double* __restrict__ pivot,
+                    double* __restrict__ osum, double* __restrict__ osumsq) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int stage_doubles = nks * NBLK * 32;
+    double* ring = reinterpret_cast<double*>(smraw);
+    double* red = ring + (size_t)nstage * stage_doubles;              // [8 warps][2][8][Kp]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + BM_WARPS * 16 * Kp);
+    uint64_t* empty = full + nstage;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = lane & 3, vr = lane >> 2;
+    const long long v = (long long)blockIdx.x * BM_VOX + warp * 8 + vr;
+    const int per0 = blockIdx.y * per_per_split;
+    const int per1 = min(nper, per0 + per_per_split);
+    const int nit = per1 - per0;
+    const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, BM_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {   // thread 0 only: stream period per0+it into slot it % nstage
+        const int slot = it % nstage;
+        mbar_expect_tx(full + slot, stage_bytes);
+        const char* src = reinterpret_cast<const char*>(coef + (size_t)(per0 + it) * stage_doubles);
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+        for (uint32_t off = 0; off < stage_bytes; off += 16384u) {
+            const uint32_t n = min(16384u, stage_bytes - off);
+            bulk_g2s(dst + off, src + off, n, full + slot);
+        }
+    };
+    if (tid == 0)
+        for (int it = 0; it < min(nstage, nit); ++it) issue(it);
+
+    // ---- A fragments: this warp's 8 voxels x all rows, resident in registers
+    double a[MAXKS];
+#pragma unroll
+    for (int s = 0; s < MAXKS; ++s) {
+        const int row = 4 * s + q;
+        a[s] = (s < nks && row < N && v < p) ? __ldg(X + (long long)row * ldx + v) : 0.0;
+    }
+
+    // ---- per-thread column bookkeeping (fixed for the whole kernel)
+    int kk[NBLK][2], bo[NBLK][2];
+    double piv[NBLK][2], s1[NBLK][2], s2[NBLK][2];
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = 8 * j + 2 * q + e;
+            kk[j][e] = c % Kp; bo[j][e] = c / Kp;
+            piv[j][e] = (pivot != nullptr && kk[j][e] < K && v < p) ? __ldg(pivot + v * K + kk[j][e]) : 0.0;
+            s1[j][e] = 0.0; s2[j][e] = 0.0;
+        }
+    const int nb = 8 * NBLK / Kp;
+
+    for (int it = 0; it < nit; ++it) {
+        const int slot = it % nstage;
+        if (tid == 0 && it > 0) {
+            // refill the slot drained in the previous iteration with period it-1+nstage
+            const int nx = it - 1 + nstage;
+            if (nx < nit) {
+                mbar_wait(empty + (it - 1) % nstage, ((it - 1) / nstage) & 1);
+                issue(nx);
+            }
+        }
+        __syncwarp();
+        mbar_wait(full + slot, (it / nstage) & 1);
+
+        double d[NBLK][2];
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j) { d[j][0] = -piv[j][0]; d[j][1] = -piv[j][1]; }
+        const double* bs = ring + (size_t)slot * stage_doubles + lane;
+#pragma unroll
+        for (int s0 = 0; s0 < MAXKS; s0 += 4) {
+            if (s0 < nks) {
+#pragma unroll
+                for (int s = s0; s < s0 + 4; ++s) {
+#pragma unroll
+                    for (int j = 0; j < NBLK; ++j) {
+                        const double b = bs[(s * NBLK + j) * 32];
+                        dmma884(d[j][0], d[j][1], a[s], b);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+
+        const int rbase = (per0 + it) * nb;
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (rbase + bo[j][e] < R) {
+                    s1[j][e] += d[j][e];
+                    s2[j][e] = fma(d[j][e], d[j][e], s2[j][e]);
+                }
+            }
+    }
+
+    // ---- fold the nb resample slots of a period onto k, in slot order (deterministic)
+    double* r1 = red + warp * (16 * Kp);
+    double* r2 = r1 + 8 * Kp;
+    for (int i = lane; i < 16 * Kp; i += 32) r1[i] = 0.0;
+    __syncwarp();
+    for (int round = 0; round < nb; ++round) {
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (bo[j][e] == round) {
+                    r1[vr * Kp + kk[j][e]] += s1[j][e];
+                    r2[vr * Kp + kk[j][e]] += s2[j][e];
+                }
+        __syncwarp();
+    }
+    const long long vbase = (long long)blockIdx.x * BM_VOX + warp * 8;
+    double* o1 = osum + (size_t)blockIdx.y * p * K;
+    double* o2 = osumsq + (size_t)blockIdx.y * p * K;
+    for (int i = lane; i < 8 * K; i += 32) {
+        const int rr = i / K, k = i % K;
+        if (vbase + rr < p) {
+            o1[(vbase + rr) * K + k] = r1[rr * Kp + k];
+            o2[(vbase + rr) * K + k] = r2[rr * Kp + k];
+        }
+    }
+}
+
+__global__ void moments_reduce_kernel(const double* __restrict__ part1, const double* __restrict__ part2, int nsplit,
+                                      long long n, double* __restrict__ sum, double* __restrict__ sumsq) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < nsplit; ++s) { a += part1[(size_t)s * n + i]; b += part2[(size_t)s * n + i]; }
+    sum[i] = a; sumsq[i] = b;
+}
+
+__global__ void boot_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, long long n,
+                                     double R, const double* __restrict__ numer, double* __restrict__ std_errs,
+                                     double* __restrict__ ratios) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = sum[i] / R;
+    double var = sumsq[i] / R - m * m;
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    std_errs[i] = sd;
+    if (ratios) ratios[i] = numer[i] / sd;
+}
+
+// explicit saliences VS[r][v][k] = sum_i X[idx_r[i], v] . E[i, k]  (reference order of operations;
+// small problems / debugging only -- writes R*p*K doubles)
+template <int KT>
+__global__ void __launch_bounds__(128) salience_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
+                                                      const double* __restrict__ E, int K,
+                                                      const int32_t* __restrict__ idx, double* __restrict__ VS) {
+    extern __shared__ __align__(16) double sms[];
+    double* Es = sms;
+    int* ids = reinterpret_cast<int*>(Es + (size_t)N * K);
+    const int r = blockIdx.y;
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) Es[i] = E[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
+    __syncthreads();
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p) return;
+    for (int k0 = 0; k0 < K; k0 += KT) {
+        double acc[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double x = __ldg(X + (long long)ids[i] * ldx + v);
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+                if (k0 + t < K) acc[t] = fma(x, Es[i * K + k0 + t], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+            if (k0 + t < K) VS[((size_t)r * p + v) * K + k0 + t] = acc[t];
+    }
+}
+
+// XL = X . V : each CTA takes a voxel chunk, V chunk staged in smem, one warp per row of X.
+constexpr int XV_CHUNK = 1024;
+template <int KT>
+__global__ void __launch_bounds__(256) xv_partial_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
+                                                        const double* __restrict__ V, int K,
+                                                        double* __restrict__ part) {
+    extern __shared__ __align__(16) double smv[];   // [XV_CHUNK][K]
+    const long long v0 = (long long)blockIdx.x * XV_CHUNK;
+    const int nv = (int)min((long long)XV_CHUNK, p - v0);
+    for (int i = threadIdx.x; i < nv * K; i += blockDim.x) smv[i] = V[v0 * K + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int row = warp; row < N; row += nw) {
+        const double* x = X + (long long)row * ldx + v0;
+        for (int k0 = 0; k0 < K; k0 += KT) {
+            double acc[KT];
+#pragma unroll
+            for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+            for (int c = lane; c < nv; c += 32) {
+                const double xv = __ldg(x + c);
+#pragma unroll
+                for (int t = 0; t < KT; ++t)
+                    if (k0 + t < K) acc[t] = fma(xv, smv[c * K + k0 + t], acc[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                double s = acc[t];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && k0 + t < K) part[((size_t)blockIdx.x * N + row) * K + k0 + t] = s;
+            }
+        }
+    }
+}
+
+__global__ void xv_reduce_kernel(const double* __restrict__ part, int nchunk, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * n + i];
+    out[i] = s;
+}
+
+template <int MAXKS, int NBLK>
+static int launch_moments(const BootPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                          int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_kernel<MAXKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)b.smem_bytes));
+    dim3 grid((unsigned)cdiv(p, BM_VOX), (unsigned)b.nsplit);
+    boot_moments_kernel<MAXKS, NBLK><<<grid, BM_THREADS, b.smem_bytes, st>>>(
+        X, ldx, N, p, coef, b.nks, b.nper, b.per_per_split, b.nstage, R, b.Kp, K, pivot, o1, o2);
+    PLSB_LAUNCH_CHECK("boot_moments_kernel");
+    return PLSB200_OK;
+}
+
+template <int MAXKS>
+static int dispatch_nblk(const BootPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                         int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    switch (b.nblk) {
+        case 1: return launch_moments<MAXKS, 1>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 2: return launch_moments<MAXKS, 2>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        default: return launch_moments<MAXKS, 3>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+    }
+}
+
+}  // namespace plsb
+
+using namespace plsb;
+
+extern "C" size_t plsb200_boot_coef_bytes(int N, int K, int R) {
+    BootPlan b;
+    if (!boot_plan(N, K, R, 1, b)) return 0;
+    return (size_t)b.nper * b.stage_doubles * sizeof(double);
+}
+
+extern "C" int plsb200_boot_coef_pack_f64(const double* E, int N, int K, const int32_t* idx, int R, double* coef,
+                                          void* stream) {
+    PLSB_CHECK_ARG(E && idx && coef, "boot_coef_pack_f64: null pointer");
+    BootPlan b;
+    if (!boot_plan(N, K, R, 1, b)) {
+        set_err("boot_coef_pack_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=320)", N, K, R);
+        return PLSB200_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * b.stage_doubles * sizeof(double), st));
+    size_t smem = (size_t)N * K * sizeof(double) + (size_t)N * sizeof(int);
+    PLSB_CUDA(cudaFuncSetAttribute(boot_coef_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    boot_coef_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nblk, b.nb, b.nks, coef);
+    PLSB_LAUNCH_CHECK("boot_coef_pack_kernel");
+    return PLSB200_OK;
+}
+
+extern "C" size_t plsb200_boot_moments_f64_workspace(int N, int64_t p, int K, int R) {
+    BootPlan b;
+    if (!boot_plan(N, K, R, p, b)) return 0;
+    return b.nsplit > 1 ? (size_t)2 * b.nsplit * p * K * sizeof(double) : 16;
+}
+
+extern "C" int plsb200_boot_moments_f64(const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R,
+                                        const double* pivot, double* sum, double* sumsq, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    PLSB_CHECK_ARG(X && coef && sum && sumsq, "boot_moments_f64: null pointer");
+    PLSB_CHECK_ARG(p > 0 && ldx >= p, "boot_moments_f64: bad shape p=%lld ldx=%lld", (long long)p, (long long)ldx);
+    BootPlan b;
+    if (!boot_plan(N, K, R, p, b)) {
+        set_err("boot_moments_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=320)", N, K, R);
+        return PLSB200_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *o1 = sum, *o2 = sumsq;
+    if (b.nsplit > 1) {
+        size_t need = (size_t)2 * b.nsplit * p * K * sizeof(double);
+        if (!workspace || workspace_bytes < need) {
+            set_err("boot_moments_f64: workspace %zu < %zu bytes", workspace_bytes, need);
+            return PLSB200_EWORKSPACE;
+        }
+        o1 = (double*)workspace;
+        o2 = o1 + (size_t)b.nsplit * p * K;
+    }
+    int rc;
+    switch (b.maxks) {
+        case 20: rc = dispatch_nblk<20>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+        case 40: rc = dispatch_nblk<40>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+        case 60: rc = dispatch_nblk<60>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+        default: rc = dispatch_nblk<80>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+    }
+    if (rc != PLSB200_OK) return rc;
+    if (b.nsplit > 1) {
+        const long long n = (long long)p * K;
+        moments_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(o1, o2, b.nsplit, n, sum, sumsq);
+        PLSB_LAUNCH_CHECK("moments_reduce_kernel");
+    }
+    return PLSB200_OK;
+}
+
+extern "C" int plsb200_boot_finalize_f64(const double* sum, const double* sumsq, int64_t p, int K, int64_t R_total,
+                                         const double* numer, double* std_errs, double* boot_ratios, void* stream) {
+    PLSB_CHECK_ARG(sum && sumsq && std_errs, "boot_finalize_f64: null pointer");
+    PLSB_CHECK_ARG(p > 0 && K > 0 && R_total > 0, "boot_finalize_f64: bad shape");
+    PLSB_CHECK_ARG(boot_ratios == nullptr || numer != nullptr, "boot_finalize_f64: ratios requested without numerator");
+    const long long n = (long long)p * K;
+    boot_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sum, sumsq, n, (double)R_total, numer,
+                                                                                  std_errs, boot_ratios);
+    PLSB_LAUNCH_CHECK("boot_finalize_kernel");
+    return PLSB200_OK;
+}
+
+extern "C" int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
+                                    const int32_t* idx, int R, double* VS, void* stream) {
+    PLSB_CHECK_ARG(X && E && idx && VS, "salience_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && R >= 0 && ldx >= p, "salience_f64: bad shape");
+    if (R == 0) return PLSB200_OK;
+    size_t smem = (size_t)N * K * sizeof(double) + (size_t)N * sizeof(int);
+    if (smem > 200 * 1024) {
+        set_err("salience_f64: N*K too large");
+        return PLSB200_EUNSUPPORTED;
+    }
+    PLSB_CUDA(cudaFuncSetAttribute(salience_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)cdiv(p, 128), (unsigned)R);
+    salience_kernel<12><<<grid, 128, smem, (cudaStream_t)stream>>>(X, N, p, ldx, E, K, idx, VS);
+    PLSB_LAUNCH_CHECK("salience_kernel");
+    return PLSB200_OK;
+}
+
+extern "C" size_t plsb200_xv_f64_workspace(int N, int64_t p, int K) {
+    if (N <= 0 || p <= 0 || K <= 0) return 0;
+    return (size_t)cdiv(p, XV_CHUNK) * N * K * sizeof(double);
+}
+
+extern "C" int plsb200_xv_f64(const double* X, int N, int64_t p, int64_t ldx, const double* V, int K, double* XL,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    PLSB_CHECK_ARG(X && V && XL && workspace, "xv_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && ldx >= p, "xv_f64: bad shape");
+    const int nchunk = (int)cdiv(p, XV_CHUNK);
+    size_t need = (size_t)nchunk * N * K * sizeof(double);
+    if (workspace_bytes < need) {
+        set_err("xv_f64: workspace %zu < %zu bytes", workspace_bytes, need);
+        return PLSB200_EWORKSPACE;
+    }
+    size_t smem = (size_t)XV_CHUNK * K * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_err("xv_f64: K=%d too large", K);
+        return PLSB200_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PLSB_CUDA(cudaFuncSetAttribute(xv_partial_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xv_partial_kernel<12><<<nchunk, 256, smem, st>>>(X, N, p, ldx, V, K, (double*)workspace);
+    PLSB_LAUNCH_CHECK("xv_partial_kernel");
+    xv_reduce_kernel<<<(unsigned)cdiv((int64_t)N * K, 256), 256, 0, st>>>((const double*)workspace, nchunk, N * K, XL);
+    PLSB_LAUNCH_CHECK("xv_reduce_kernel");
+    return PLSB200_OK;
+}

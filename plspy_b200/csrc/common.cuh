@@ -1,0 +1,135 @@
+// Shared host/device helpers for libplsb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/plsb200.h"
+
+namespace plsb {
+
+// ---------------------------------------------------------------- host side
+char* err_buf();
+void set_err(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PLSB_CHECK_ARG(cond, ...)                      \
+    do {                                               \
+        if (!(cond)) {                                 \
+            plsb::set_err(__VA_ARGS__);                \
+            return PLSB200_EINVAL;                     \
+        }                                              \
+    } while (0)
+
+#define PLSB_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            plsb::set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PLSB200_ECUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+#define PLSB_LAUNCH_CHECK(name)                                                             \
+    do {                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) {                                                           \
+            plsb::set_err("launch of %s failed: %s", name, cudaGetErrorString(e__));        \
+            return PLSB200_ECUDA;                                                           \
+        }                                                                                   \
+        plsb::count_launch();                                                               \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4 -- the only native f64
+// MMA shape on sm_100a; the m16n8k{4,8,16} PTX shapes lower to sequences of it).
+//   a : A[row = lane/4][k = lane%4]      b : B[k = lane%4][col = lane/4]
+//   d0,d1 : D[row = lane/4][col = 2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared, completion signalled on an mbarrier (bytes multiple of 16, both 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- Ampere-style cp.async with zero fill (SASS LDGSTS) ----
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* dst_smem, const void* src_gmem, int src_bytes) {
+    if constexpr (BYTES == 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                     "r"(src_bytes)
+                     : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                     "r"(src_bytes)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+#endif  // __CUDACC__
+}  // namespace plsb

@@ -1,0 +1,192 @@
+"""Device-side resampling engine: thin Python object over the C ABI (include/plsb200.h).
+
+PyTorch is used for device memory, streams and (in `dist.py`) torch.distributed only; every number is
+produced by the hand-written kernels of libplsb200.so.  There is no CPU path: constructing an Engine
+without a CUDA device raises.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "plspy_b200 needs a CUDA device (B200, sm_100a): its resampling path is hand-written CUDA "
+            "with no CPU fallback."
+        )
+
+
+class Engine:
+    """Holds X (N x p, float64) on one GPU together with its Gram matrix and runs the batched kernels.
+
+    Replaces, for one analysis, the per-iteration bodies of `_permutation_test` / `_bootstrap_test`
+    (plspy/core/bootstrap_permutation.py:323-452, 537-675).
+    """
+
+    def __init__(self, X, device=None):
+        _require_cuda()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.X = self.to_device(X, F64)
+        if self.X.dim() != 2:
+            raise ValueError("X must be 2-dimensional")
+        self.N, self.p = int(self.X.shape[0]), int(self.X.shape[1])
+        self.ldx = int(self.X.stride(0))
+        self._G = None
+        self.h2d_bytes = self.X.numel() * 8 if not (torch.is_tensor(X) and X.is_cuda) else 0
+
+    # ------------------------------------------------------------------ plumbing
+    def to_device(self, a, dtype):
+        if torch.is_tensor(a):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        elif t.device != self.device:
+            t = t.to(self.device)
+        return t.contiguous()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _empty(self, *shape, dtype=F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _ws(self, nbytes):
+        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+
+    @staticmethod
+    def _p(t):
+        return t.data_ptr() if t is not None else None
+
+    # ------------------------------------------------------------------ kernels
+    @property
+    def G(self):
+        """K1: G = X X^T (N x N)."""
+        if self._G is None:
+            with torch.cuda.device(self.device):
+                need = lib.plsb200_gram_f64_workspace(self.N, self.p)
+                ws = self._ws(need)
+                G = self._empty(self.N, self.N)
+                check(lib.plsb200_gram_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(G), self._p(ws),
+                                           ws.numel(), self._stream()), "gram_f64")
+            self._G = G
+        return self._G
+
+    def xv(self, V):
+        """XL = X @ V (N x K)."""
+        V = self.to_device(V, F64)
+        K = int(V.shape[1])
+        with torch.cuda.device(self.device):
+            ws = self._ws(lib.plsb200_xv_f64_workspace(self.N, self.p, K))
+            out = self._empty(self.N, K)
+            check(lib.plsb200_xv_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(V), K, self._p(out),
+                                     self._p(ws), ws.numel(), self._stream()), "xv_f64")
+        return out
+
+    def nspace(self, E, idx, Lmat=None):
+        """d2[r,k] = ||X^T C_r[:,k]||^2 and (optionally) T[r] = Lmat G C_r diag(1/sqrt(d2))."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        assert idx.shape[1] == self.N and E.shape[0] == self.N
+        d2 = self._empty(R, K)
+        T = None; Kt = 0
+        if Lmat is not None:
+            Lmat = self.to_device(Lmat, F64); Kt = int(Lmat.shape[0])
+            assert Lmat.shape[1] == self.N
+            T = self._empty(R, Kt, K)
+        G = self.G
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_nspace_f64(self._p(G), self.N, self._p(E), K, self._p(idx), R, self._p(Lmat), Kt,
+                                         self._p(d2), self._p(T), self._stream()), "nspace_f64")
+        return d2, T
+
+    def perm_count(self, d2, s_ref, totcov_ref, thresh, counts=None, mb_total=None):
+        d2 = self.to_device(d2, F64)
+        R, K = int(d2.shape[0]), int(d2.shape[1])
+        s_ref = self.to_device(s_ref, F64); totcov_ref = self.to_device(totcov_ref, F64)
+        if mb_total is not None:
+            mb_total = self.to_device(mb_total, F64)
+        if counts is None:
+            counts = torch.zeros(2 * K, dtype=torch.int64, device=self.device)
+        s_hat = self._empty(R, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_perm_count_f64(self._p(d2), R, K, self._p(s_ref), self._p(totcov_ref), float(thresh),
+                                             self._p(mb_total), self._p(counts), self._p(s_hat), self._stream()),
+                  "perm_count_f64")
+        return counts, s_hat
+
+    def uhat(self, XL, Lop, idx):
+        XL = self.to_device(XL, F64); Lop = self.to_device(Lop, F64); idx = self.to_device(idx, I32)
+        R, K, Ku = int(idx.shape[0]), int(XL.shape[1]), int(Lop.shape[0])
+        out = self._empty(R, Ku, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_uhat_f64(self._p(XL), self.N, K, self._p(Lop), Ku, self._p(idx), R, self._p(out),
+                                       self._stream()), "uhat_f64")
+        return out
+
+    KMAX = 24   # columns per boot_moments launch
+
+    def boot_moments(self, E, idx, pivot=None):
+        """K4: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 with VS_r = X^T scatter(E, idx_r); p x K each."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        if pivot is not None:
+            pivot = self.to_device(pivot, F64)
+        if K > self.KMAX:   # columns are independent: split wide problems
+            parts = []
+            for k0 in range(0, K, self.KMAX):
+                sl = slice(k0, min(K, k0 + self.KMAX))
+                parts.append(self.boot_moments(E[:, sl].contiguous(), idx,
+                                               None if pivot is None else pivot[:, sl].contiguous()))
+            return torch.cat([a for a, _ in parts], dim=1), torch.cat([b for _, b in parts], dim=1)
+        with torch.cuda.device(self.device):
+            nbytes = lib.plsb200_boot_coef_bytes(self.N, K, R)
+            if nbytes == 0:
+                raise _lib.PlsB200Error(f"boot_moments: unsupported shape N={self.N} K={K} R={R}")
+            coef = self._ws(nbytes)
+            check(lib.plsb200_boot_coef_pack_f64(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
+                                                 self._stream()), "boot_coef_pack_f64")
+            ws = self._ws(lib.plsb200_boot_moments_f64_workspace(self.N, self.p, K, R))
+            s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
+            check(lib.plsb200_boot_moments_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(coef), K, R,
+                                               self._p(pivot), self._p(s1), self._p(s2), self._p(ws), ws.numel(),
+                                               self._stream()), "boot_moments_f64")
+        return s1, s2
+
+    def boot_finalize(self, s1, s2, R_total, numer=None):
+        K = int(s1.shape[1])
+        se = self._empty(self.p, K)
+        br = self._empty(self.p, K) if numer is not None else None
+        if numer is not None:
+            numer = self.to_device(numer, F64)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_boot_finalize_f64(self._p(s1), self._p(s2), self.p, K, int(R_total), self._p(numer),
+                                                self._p(se), self._p(br), self._stream()), "boot_finalize_f64")
+        return se, br
+
+    def colstd(self, A):
+        A = self.to_device(A, F64)
+        R = int(A.shape[0]); M = int(A.numel() // R)
+        out = self._empty(*A.shape[1:])
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_colstd_f64(self._p(A), R, M, self._p(out), self._stream()), "colstd_f64")
+        return out
+
+    def salience(self, E, idx):
+        """Explicit VS[r] = X^T scatter(E, idx_r) (R x p x K) -- small problems only."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        out = self._empty(R, self.p, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_salience_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(E), K, self._p(idx), R,
+                                           self._p(out), self._stream()), "salience_f64")
+        return out

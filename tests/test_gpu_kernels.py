@@ -1,0 +1,173 @@
+"""Kernel-level parity (through the C ABI) against plain numpy on the same seeded inputs.
+Tolerances: FP64 kernels vs float64 numpy, differences are summation order only -> 1e-11 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _scatter(E, idx):
+    C = np.zeros_like(E)
+    np.add.at(C, idx, E)
+    return C
+
+
+def _mk(N, p, K, R, seed, boot=True, offset=0.0):
+    rs = np.random.RandomState(seed)
+    X = rs.standard_normal((N, p)) + offset
+    E = rs.standard_normal((N, K)) / np.sqrt(N)
+    if boot:
+        idx = rs.randint(0, N, size=(R, N))
+    else:
+        idx = np.array([rs.permutation(N) for _ in range(R)])
+    return X, E, idx.astype(np.int32)
+
+
+@pytest.mark.parametrize("N,p", [(60, 1000), (300, 4099), (37, 513), (130, 64), (64, 7)])
+def test_gram(torch_cuda, N, p):
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(N + p)
+    X = rs.standard_normal((N, p)) + 3.0
+    G = Engine(X).G.cpu().numpy()
+    ref = X @ X.T
+    np.testing.assert_allclose(G, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    assert np.array_equal(G, G.T)
+
+
+def test_gram_deterministic(torch_cuda):
+    from plspy_b200.engine import Engine
+    X = np.random.RandomState(3).standard_normal((90, 20000))
+    a = Engine(X).G.cpu().numpy(); b = Engine(X).G.cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+def test_gram_strided_odd(torch_cuda):
+    """odd leading dimension -> 8-byte cp.async path"""
+    import torch
+    from plspy_b200.engine import Engine
+    X = np.random.RandomState(4).standard_normal((50, 1001))
+    e = Engine(X)
+    assert e.ldx == 1001
+    np.testing.assert_allclose(e.G.cpu().numpy(), X @ X.T, rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("N,K,R,boot", [(60, 6, 33, False), (60, 6, 17, True), (300, 12, 9, True),
+                                        (45, 3, 8, True), (120, 24, 5, True), (96, 30, 4, True)])
+def test_nspace(torch_cuda, N, K, R, boot):
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(N, 700, K, R, 10 + N + K, boot)
+    rs = np.random.RandomState(1)
+    L = rs.standard_normal((5, N))
+    eng = Engine(X)
+    d2, T = eng.nspace(E, idx, L)
+    d2 = d2.cpu().numpy(); T = T.cpu().numpy()
+    for r in range(R):
+        VS = X.T @ _scatter(E, idx[r])
+        nrm2 = np.sum(VS ** 2, axis=0)
+        np.testing.assert_allclose(d2[r], nrm2, rtol=1e-11)
+        Tref = L @ (X @ (VS / np.sqrt(nrm2)))
+        np.testing.assert_allclose(T[r], Tref, rtol=1e-10, atol=1e-10)
+
+
+def test_perm_count(torch_cuda):
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(7)
+    R, K = 1000, 7
+    d2 = rs.rand(R, K) * 4
+    d2[::13, 2] = 1e-30          # below-threshold values are zeroed
+    d2[5, 1] = -1e-18            # rounding noise below zero must not produce NaN
+    s = np.sqrt(rs.rand(K) * 4); s[-1] = 0.0
+    tot = np.cumsum((s ** 2)[::-1])[::-1].copy()
+    eng = Engine(np.zeros((4, 4)))
+    counts, s_hat = eng.perm_count(d2, s, tot, 1e-12)
+    sh = np.sqrt(np.maximum(d2, 0)); sh[np.abs(sh) < 1e-12] = 0
+    np.testing.assert_allclose(s_hat.cpu().numpy(), sh, rtol=1e-15)
+    c = counts.cpu().numpy()
+    assert np.array_equal(c[:K], (sh >= s).sum(0))
+    tails = np.cumsum((sh ** 2)[:, ::-1], axis=1)[:, ::-1]
+    assert np.array_equal(c[K:], (tails >= tot).sum(0))
+    # multiblock rescale
+    tot_r = rs.rand(R) * 10 + 1
+    counts2, s_hat2 = eng.perm_count(d2, s, tot, 0.0, mb_total=tot_r)
+    v = np.maximum(d2, 0)
+    ref = np.sqrt(v ** 2 / np.sum(v ** 2, axis=1, keepdims=True) * tot_r[:, None])
+    np.testing.assert_allclose(s_hat2.cpu().numpy(), ref, rtol=1e-13)
+
+
+@pytest.mark.parametrize("N,p,K,R", [
+    (60, 1000, 6, 50),      # cfg1-like, nb=4 per period
+    (300, 777, 12, 21),     # target shape, odd p, R not a multiple of nb
+    (300, 130, 12, 160),    # enough periods to trigger nsplit>1 on few tiles
+    (36, 300, 3, 19),       # nb=8
+    (120, 500, 24, 7),      # nb=1
+    (52, 200, 5, 11),       # K padded to 6
+    (77, 200, 16, 9),       # NBLK=2
+    (20, 100, 1, 30),       # K=1
+    (100, 260, 7, 13),      # K padded to 8
+    (64, 100, 30, 6),       # K > 24: column chunks
+])
+def test_boot_moments(torch_cuda, N, p, K, R):
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(N, p, K, R, 99 + N + K, True, offset=2.0)
+    rs = np.random.RandomState(5)
+    pivot = rs.standard_normal((p, K))
+    eng = Engine(X)
+    VS = np.stack([X.T @ _scatter(E, idx[r]) for r in range(R)])
+    for pv in (None, pivot):
+        s1, s2 = eng.boot_moments(E, idx, pv)
+        d = VS - (0 if pv is None else pv)
+        scale = np.abs(d).max()
+        np.testing.assert_allclose(s1.cpu().numpy(), d.sum(0), rtol=1e-11, atol=1e-11 * scale * R)
+        np.testing.assert_allclose(s2.cpu().numpy(), (d ** 2).sum(0), rtol=1e-11, atol=1e-11 * scale ** 2 * R)
+    se, br = eng.boot_finalize(s1, s2, R, numer=pivot)
+    np.testing.assert_allclose(se.cpu().numpy(), VS.std(0), rtol=1e-9)
+    np.testing.assert_allclose(br.cpu().numpy(), pivot / VS.std(0), rtol=1e-9)
+    # the explicit-salience kernel agrees too
+    np.testing.assert_allclose(eng.salience(E, idx).cpu().numpy(), VS, rtol=1e-11, atol=1e-11 * np.abs(VS).max())
+
+
+def test_boot_moments_large_deterministic(torch_cuda):
+    """full-size voxel tile count, moments reproducible bit for bit"""
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(300, 20000, 12, 64, 1234, True)
+    eng = Engine(X)
+    a1, a2 = eng.boot_moments(E, idx)
+    b1, b2 = eng.boot_moments(E, idx)
+    import torch
+    assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    v = np.arange(0, 20000, 997)
+    VS = np.stack([X[:, v].T @ _scatter(E, idx[r]) for r in range(64)])
+    np.testing.assert_allclose(a1.cpu().numpy()[v], VS.sum(0), rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(a2.cpu().numpy()[v], (VS ** 2).sum(0), rtol=1e-11)
+
+
+def test_xv_uhat_colstd(torch_cuda):
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(11)
+    N, p, K = 75, 3001, 6
+    X = rs.standard_normal((N, p)); V = rs.standard_normal((p, K))
+    eng = Engine(X)
+    XL = eng.xv(V)
+    np.testing.assert_allclose(XL.cpu().numpy(), X @ V, rtol=1e-11, atol=1e-10)
+    Lop = rs.standard_normal((K, N))
+    idx = rs.randint(0, N, size=(9, N)).astype(np.int32)
+    U = eng.uhat(XL, Lop, idx).cpu().numpy()
+    for r in range(9):
+        np.testing.assert_allclose(U[r], Lop @ (X @ V)[idx[r]], rtol=1e-10, atol=1e-10)
+    A = rs.standard_normal((40, 6, 5))
+    np.testing.assert_allclose(eng.colstd(A).cpu().numpy(), A.std(0), rtol=1e-12)
+
+
+def test_error_reporting(torch_cuda):
+    from plspy_b200.engine import Engine
+    from plspy_b200._lib import PlsB200Error
+    eng = Engine(np.zeros((400, 10)))
+    with pytest.raises(PlsB200Error):
+        eng.boot_moments(np.zeros((400, 3)), np.zeros((2, 400), np.int32))   # N > 320 not supported yet
