@@ -1,0 +1,56 @@
+"""Resample-level data parallelism: X replicated, the resample index range is
+cut into one contiguous shard per rank, and only the tiny permutation counters, the two p x K moment
+matrices and the per-resample K x K outputs cross NVLink, through torch.distributed (NCCL on GPUs;
+the same code runs under gloo on CPU tensors for the host-logic tests).
+"""
+import torch
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard(n, rank=None, size=None):
+    """Contiguous [lo, hi) slice of range(n) owned by `rank`; sizes differ by at most one."""
+    if rank is None:
+        rank, size = world()
+    base, rem = divmod(int(n), int(size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks (no-op for a single process). Integer counters reduce exactly."""
+    import torch.distributed as dist
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_packed_(tensors):
+    """ONE all-reduce for several same-dtype tensors (counts, or [sum | sumsq]): packs, reduces, unpacks."""
+    if world()[1] == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    allreduce_sum_(flat)
+    o = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[o:o + n].view_as(t))
+        o += n
+    return tensors
+
+
+def gather_rows(local, n_total, lo):
+    """Assemble per-resample rows computed on each rank's shard into the full [n_total, ...] tensor on
+    every rank: each rank writes its rows into a zero tensor and the ranks are summed (exact: every
+    element has exactly one non-zero contribution)."""
+    if world()[1] == 1:
+        return local
+    full = torch.zeros((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full[lo:lo + local.shape[0]] = local
+    return allreduce_sum_(full)

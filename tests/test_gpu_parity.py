@@ -1,0 +1,123 @@
+"""Parity of the CUDA path (through plspy_b200.PLS -> C ABI) against (a) the golden fixtures recorded
+from the real reference and (b) the oracle on larger seeded problems.
+
+Tolerances (BASELINE.json north_star): permutation p-values exact (up to documented ties); singular
+values 1e-10 relative (FP64 mode); bootstrap ratios 1e-4 -- the FP64 path is held to 1e-8 here."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_DIR, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+TASK_CASES = [c for c in golden_cases() if c.startswith(("mct", "cst"))]
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+
+
+def _run_product(g, **extra):
+    import plspy_b200
+    method = str(g["method"])
+    kw = dict(num_perm=int(g["nperm"]), num_boot=int(g["nboot"]), pls_method=method, CI=float(g["CI"]))
+    if method in ("mct", "cst", "mb", "cmb"):
+        kw["mctype"] = int(g["mctype"])
+    if "Y" in g:
+        kw["Y"] = g["Y"].copy()
+    if "contrasts_in" in g:
+        kw["contrasts"] = g["contrasts_in"].copy()
+    if "bscan" in g:
+        kw["bscan"] = [int(b) for b in g["bscan"]]
+    kw.update(extra)
+    np.random.seed(int(g["np_seed"]))
+    return plspy_b200.PLS(g["X"].copy(), tuple(int(n) for n in g["groups"]), int(g["C"]), **kw)
+
+
+@pytest.mark.parametrize("name", TASK_CASES)
+def test_task_methods_match_reference_golden(name):
+    g = _load(name)
+    res = _run_product(g)
+    rt = res.resample_tests
+    live = np.abs(g["s"]) > 1e-8
+    np.testing.assert_allclose(res.s, g["s"], rtol=1e-10, atol=1e-10)
+    # indices drawn by the product's host generator == the reference's own draws
+    np.testing.assert_array_equal(rt.perm_debug_dict["indices"], g["perm_idx_task"])
+    np.testing.assert_array_equal(rt.boot_debug_dict["indices"], g["boot_idx"])
+    # permutation p-values: exact
+    np.testing.assert_array_equal(rt.permute_ratio, g["permute_ratio"])
+    np.testing.assert_array_equal(rt.stepdown_ratio, g["stepdown_ratio"])
+    if g["perm_s_last"].size:
+        np.testing.assert_allclose(rt.perm_debug_dict["s_list"][-1][live], g["perm_s_last"][live], rtol=1e-10)
+    np.testing.assert_allclose(rt.perm_debug_dict["sum_s"], g["perm_sum_perm"], rtol=1e-9)
+    # bootstrap
+    np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], g["boot_ratios"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(rt.conf_ints[1][:, live], g["conf_hi"][:, live], rtol=1e-8, atol=1e-9)
+    if "left_sv_sampled" in g:
+        np.testing.assert_allclose(rt.boot_debug_dict["left_sv_sampled"][:, :, live],
+                                   g["left_sv_sampled"][:, :, live], rtol=1e-8, atol=1e-9)
+    p = g["X"].shape[1]
+    right = rt.boot_debug_dict["right_sv_sampled"]
+    np.testing.assert_allclose(right[:, :: max(1, p // 16), :][:, :, live], g["right_sv_sub"][:, :, live],
+                               rtol=1e-8, atol=1e-9)
+    # result-field contract (App. D)
+    for f in ("pls_alg", "X", "groups_sizes", "num_groups", "num_conditions", "cond_order", "num_perm",
+              "num_boot", "CI", "s", "U", "V", "X_latent", "resample_tests"):
+        assert hasattr(res, f), f
+    np.testing.assert_allclose(np.abs(res.U[:, live]), np.abs(g["U_brain"][:, live]), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("method,mctype,groups,C,p", [
+    ("mct", 0, (10, 10), 3, 10000),      # BASELINE cfg 1 shape (reduced iterations)
+    ("mct", 2, (7, 9, 8), 4, 3000),
+    ("cst", 0, (8, 8, 8), 4, 5000),
+])
+def test_task_methods_match_oracle(method, mctype, groups, C, p):
+    """Same inputs, same index matrices (passed in), 150 permutations / 150 bootstraps."""
+    import plspy_b200
+    rs = np.random.RandomState(2026 + p)
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p))
+    row = 0
+    for gsz in groups:
+        for c in range(C):
+            X[row:row + gsz, : p // 20] += 0.5 * rs.standard_normal(p // 20)
+            row += gsz
+    contrasts = np.linalg.qr(rs.standard_normal((len(groups) * C, 3)))[0] if method == "cst" else None
+    np.random.seed(42)
+    o = oracle.run_full(method, X.copy(), groups, C, contrasts=contrasts, mctype=mctype, nperm=150, nboot=150)
+    kw = dict(num_perm=150, num_boot=150, mctype=mctype, pls_method=method,
+              perm_indices=o["perm_idx_task"], boot_indices=o["boot_idx"])
+    if contrasts is not None:
+        kw["contrasts"] = contrasts
+    res = plspy_b200.PLS(X.copy(), groups, C, **kw)
+    rt = res.resample_tests
+    live = np.abs(o["s"]) > 1e-8
+    np.testing.assert_array_equal(rt.permute_ratio, o["perm"]["permute_ratio"])
+    np.testing.assert_array_equal(rt.stepdown_ratio, o["perm"]["stepdown_ratio"])
+    np.testing.assert_allclose(rt.perm_debug_dict["s_list"][:, live], o["perm"]["s_hat"][:, live], rtol=1e-10)
+    np.testing.assert_allclose(rt.std_errs[:, live], o["boot"]["std_errs"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.conf_ints[0][:, live], o["boot"]["conf_ints"][0][:, live], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(rt.boot_debug_dict["Tdistrib"][:, :, live], o["boot"]["Tdistrib"][:, :, live],
+                               rtol=1e-8, atol=1e-9)
+
+
+def test_na_placeholders_and_no_gpu_work_when_skipped():
+    import plspy_b200
+    g = _load("mct_m0_bal")
+    res = _run_product(g, num_perm=0, num_boot=0)
+    assert res.resample_tests.permute_ratio == "NA" and res.resample_tests.std_errs == "NA"
+    assert res.resample_tests.conf_ints == ["NA", "NA"]
+
+
+def test_unimplemented_methods_fail_loudly():
+    import plspy_b200
+    g = _load("rb_bal")
+    with pytest.raises(plspy_b200.exceptions.NotImplementedError):
+        _run_product(g)
