@@ -94,6 +94,20 @@ def _stepdown_tail(s):
     return np.cumsum((np.asarray(s, dtype=float) ** 2)[::-1])[::-1].copy()
 
 
+def _index_shard(eng, indices, niter, lo, hi):
+    """Rows [lo, hi) of the first `niter` index vectors as an int32 device tensor; `indices` may be a
+    numpy array, a host tensor (pinned or not) or a device tensor."""
+    if torch.is_tensor(indices):
+        return eng.to_device(indices[lo:min(hi, niter)], torch.int32)
+    return eng.to_device(np.asarray(indices)[lo:min(hi, niter)], torch.int32)
+
+
+def _indices_to_host(indices, niter):
+    if torch.is_tensor(indices):
+        return indices[:niter].cpu().numpy()
+    return np.asarray(indices)[:niter]
+
+
 def _task_operators(pls_alg, cond_order, mctype, U, contrast):
     """Row-space pull-back of the design-side weights: E = Lop^T @ Ucoef (N x K).
     mct: Lop = centring operator, Ucoef = U (bootstrap_permutation.py:385-387, 404);
@@ -162,12 +176,11 @@ class _ResampleTestPLS(ResampleTest):
         totcov_org = _stepdown_tail(org_s)
         if indices is None:
             indices = resample.permutation_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)[0]
-        idx = np.ascontiguousarray(np.asarray(indices)[:niter], dtype=np.int32)
         Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
         K = E.shape[1]
 
         lo, hi = dist.shard(niter)
-        idx_dev = eng.to_device(idx[lo:hi], torch.int32)
+        idx_dev = _index_shard(eng, indices, niter, lo, hi)
         d2, _ = eng.nspace(E, idx_dev)
         counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg == "mct" else 0.0)
         dist.allreduce_sum_(counts)
@@ -181,12 +194,12 @@ class _ResampleTestPLS(ResampleTest):
         debug = _LazyDebugDict()
         debug["s_list"] = s_list                               # row i = s_hat of permutation i (:439-441)
         debug["sum_perm"] = np.sum(s_list ** 2, axis=1)        # key names swapped in the reference (:459-460)
-        debug["indices"] = idx
+        debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
 
         def _sum_sq_crossblock():                              # sum(permuted**2) (:399): trace(Lop S G S^T Lop^T)
             if dist.world()[1] > 1:
                 raise RuntimeError("perm_debug_dict['sum_s'] is only available in single-process runs")
-            d2f, _ = eng.nspace(np.ascontiguousarray(Lop.T), eng.to_device(idx, torch.int32))
+            d2f, _ = eng.nspace(np.ascontiguousarray(Lop.T), _index_shard(eng, indices, niter, 0, niter))
             return d2f.sum(dim=1).cpu().numpy()
         debug.set_lazy("sum_s", _sum_sq_crossblock)
         return permute_ratio, stepdown_ratio, debug
@@ -200,19 +213,18 @@ class _ResampleTestPLS(ResampleTest):
         eng = engine if engine is not None else Engine(X)
         if indices is None:
             indices = resample.bootstrap_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)[0]
-        idx = np.ascontiguousarray(np.asarray(indices)[:niter], dtype=np.int32)
         Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
         Abar = class_functions._cell_mean_operator(cond_order)
-        V = np.asarray(V, dtype=float)
         # numerator of the bootstrap ratios = the original salience (:700-703); also the pivot that keeps
-        # the running sum of squares well conditioned
-        numer = eng.to_device(V * s if contrast is None else V, torch.float64)
+        # the running sum of squares well conditioned.  V may already be a device tensor.
+        Vd = eng.to_device(V, torch.float64)
+        numer = Vd * eng.to_device(np.asarray(s, dtype=float), torch.float64) if contrast is None else Vd
 
         lo, hi = dist.shard(niter)
-        idx_dev = eng.to_device(idx[lo:hi], torch.int32)
+        idx_dev = _index_shard(eng, indices, niter, lo, hi)
         d2, Tdist = eng.nspace(E, idx_dev, Lmat=Abar)                       # Tdistrib (:633-634, :665-666)
         if pls_alg == "mct":
-            XL = eng.xv(V)                                                  # X @ V once
+            XL = eng.xv(Vd)                                                 # X @ V once
             left = eng.uhat(XL, Lop, idx_dev)                               # U_hat (:617, :631)
         else:
             left = None
@@ -233,14 +245,14 @@ class _ResampleTestPLS(ResampleTest):
         debug["left_sv_sampled"] = (left.cpu().numpy() if left is not None
                                     else np.zeros((niter, Ucoef.shape[0], Ucoef.shape[1])))
         debug["Tdistrib"] = Tdist.cpu().numpy()
-        debug["indices"] = idx
+        debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
 
         def _right():   # the reference's B x p x K cube, only on request
             nbytes = niter * eng.p * E.shape[1] * 8
             if nbytes > (2 << 30):
                 raise MemoryError(f"right_sv_sampled would need {nbytes / 2**30:.1f} GiB; the B200 path "
                                   "accumulates its moments on the fly instead of storing it")
-            return eng.salience(E, eng.to_device(idx, torch.int32)).cpu().numpy()
+            return eng.salience(E, _index_shard(eng, indices, niter, 0, niter)).cpu().numpy()
         debug.set_lazy("right_sv_sampled", _right)
         return conf_int, std_errs.cpu().numpy(), boot_ratios.cpu().numpy(), debug
 

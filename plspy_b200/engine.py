@@ -38,6 +38,7 @@ class Engine:
         self.N, self.p = int(self.X.shape[0]), int(self.X.shape[1])
         self.ldx = int(self.X.stride(0))
         self._G = None
+        self.kernel_events = None     # set to {} to record CUDA events around named kernels (bench.py)
         self.h2d_bytes = self.X.numel() * 8 if not (torch.is_tensor(X) and X.is_cuda) else 0
 
     # ------------------------------------------------------------------ plumbing
@@ -66,6 +67,19 @@ class Engine:
     @staticmethod
     def _p(t):
         return t.data_ptr() if t is not None else None
+
+    def _mark(self, name):
+        """CUDA event on the launching stream, kept only when kernel_events is enabled."""
+        if self.kernel_events is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self.kernel_events.setdefault(name, []).append(ev)
+
+    def kernel_ms(self, name):
+        """Durations (ms) of the launches bracketed by _mark(name) pairs; call after a synchronize."""
+        ev = (self.kernel_events or {}).get(name, [])
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev) - 1, 2)]
 
     # ------------------------------------------------------------------ kernels
     @property
@@ -157,9 +171,11 @@ class Engine:
                                                  self._stream()), "boot_coef_pack_f64")
             ws = self._ws(lib.plsb200_boot_moments_f64_workspace(self.N, self.p, K, R))
             s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
+            self._mark("boot_moments")
             check(lib.plsb200_boot_moments_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(coef), K, R,
                                                self._p(pivot), self._p(s1), self._p(s2), self._p(ws), ws.numel(),
                                                self._stream()), "boot_moments_f64")
+            self._mark("boot_moments")
         return s1, s2
 
     def boot_finalize(self, s1, s2, R_total, numer=None):

@@ -1,0 +1,171 @@
+"""CPU tests of the host side of the drop-in: operators, RNG-order index generation, the one-off
+analysis fields of the six method classes (against the reference's golden fixtures), argument
+validation and the loud failure without a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_DIR, golden_cases
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+
+
+@pytest.mark.parametrize("mctype", [0, 1, 2, 3])
+@pytest.mark.parametrize("groups,C", [((5, 5), 3), ((4, 7, 3), 2), ((6,), 4)])
+def test_centring_operator_matches_oracle(mctype, groups, C):
+    from plspy_b200 import class_functions as cf
+    co = np.array([[n] * C for n in groups])
+    X = np.random.RandomState(1).standard_normal((co.sum(), 40)) + 5.0
+    A = cf._centring_operator(co, mctype)
+    np.testing.assert_allclose(A @ X, oracle.mean_centre(X, co, mctype), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(A.sum(axis=1), 0, atol=1e-14)          # rows sum to zero
+    np.testing.assert_allclose(cf._cell_mean_operator(co) @ X, oracle.group_condition_means(X, co), rtol=1e-13)
+    means, mc = cf._mean_centre(X, co, mctype)
+    assert means.shape == mc.shape == (co.size, 40)
+
+
+def test_behaviour_builders_match_oracle():
+    from plspy_b200 import class_functions as cf
+    co = np.array([[5, 5, 5], [7, 7, 7]])
+    rs = np.random.RandomState(2)
+    X = rs.standard_normal((36, 30)); Y = rs.standard_normal((36, 3))
+    X[:5, 4] = 1.0                                                     # constant column in one block -> 0 via nan_to_num
+    np.testing.assert_allclose(cf._compute_corr(X, Y, co), oracle.compute_corr(X, Y, co), rtol=1e-12, atol=1e-14)
+    m = oracle.bscan_mask(co, [1, 2])
+    for alg in ("mb", "cmb"):
+        a = cf._create_multiblock(X, co, alg, [1, 2], 0, Xbscan=X[m], Ybscan=Y[m])
+        b = oracle.create_multiblock(X, co, alg, [1, 2], 0, Xbscan=X[m], Ybscan=Y[m])
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_index_generation_reproduces_reference_draws(name):
+    """np.random.seed(k) + the product's host generators == the index vectors the reference drew."""
+    from plspy_b200 import resample
+    g = _load(name)
+    method = str(g["method"])
+    co = np.array([[int(n)] * int(g["C"]) for n in g["groups"]])
+    Y = g.get("Y")
+    bscan = [int(b) for b in g["bscan"]] if "bscan" in g else (list(range(int(g["C"]))) if method in ("mb", "cmb") else None)
+    Yb = Y[oracle.bscan_mask(co, bscan)] if method in ("mb", "cmb") else None
+    np.random.seed(int(g["np_seed"]))
+    if int(g["nperm"]):
+        t, b = resample.permutation_indices(method, int(g["nperm"]), co, Y=Y, bscan=bscan, Ybscan=Yb)
+        if g["perm_idx_task"].size:
+            np.testing.assert_array_equal(t, g["perm_idx_task"])
+            assert t.dtype == np.int32
+        if g["perm_idx_beh"].size:
+            np.testing.assert_array_equal(b, g["perm_idx_beh"])
+    if int(g["nboot"]):
+        m, b = resample.bootstrap_indices(method, int(g["nboot"]), co, Y=Y, bscan=bscan, Ybscan=Yb)
+        if method in ("mb", "cmb"):
+            np.testing.assert_array_equal(m, g["boot_idx_task"]); np.testing.assert_array_equal(b, g["boot_idx_beh"])
+        else:
+            np.testing.assert_array_equal(m, g["boot_idx"])
+
+
+def test_index_structure():
+    """Permutations are bijections that keep nothing but the multiset; bootstraps pick whole subjects
+    within a group, the same subjects for every condition."""
+    from plspy_b200 import resample
+    co = np.array([[4, 4, 4], [6, 6, 6]])
+    np.random.seed(0)
+    t, _ = resample.permutation_indices("mct", 20, co)
+    assert t.shape == (20, 30) and all(sorted(r) == list(range(30)) for r in t)
+    b, _ = resample.bootstrap_indices("mct", 20, co)
+    for r in b:
+        g0 = r[:12].reshape(3, 4); g1 = r[12:].reshape(3, 6)
+        assert np.array_equal(g0[1] - 4, g0[0]) and np.array_equal(g0[2] - 8, g0[0]) and g0[0].max() < 4
+        assert np.array_equal(g1[1] - 6, g1[0]) and g1[0].min() >= 12 and g1[0].max() < 18
+
+
+def test_zero_std_behaviour_is_redrawn_then_raises():
+    from plspy_b200 import resample
+    co = np.array([[3, 3]])
+    Y = np.ones((6, 1))                      # every resample has a zero-std column
+    with pytest.raises(Exception, match="behaviour data"):
+        resample.permutation_indices("rb", 1, co, Y=Y)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_one_off_analysis_fields_match_reference(name):
+    """PLS(..., num_perm=0, num_boot=0) needs no GPU; its result fields equal the reference's."""
+    import plspy_b200
+    g = _load(name)
+    method = str(g["method"])
+    kw = dict(num_perm=0, num_boot=0, pls_method=method)
+    if method in ("mct", "cst", "mb", "cmb"):
+        kw["mctype"] = int(g["mctype"])
+    if "Y" in g:
+        kw["Y"] = g["Y"].copy()
+    if "contrasts_in" in g:
+        kw["contrasts"] = g["contrasts_in"].copy()
+    if "bscan" in g:
+        kw["bscan"] = [int(b) for b in g["bscan"]]
+    res = plspy_b200.PLS(g["X"].copy(), tuple(int(n) for n in g["groups"]), int(g["C"]), **kw)
+    live = np.abs(g["s"]) > 1e-8
+    s_ref = g["s"].copy()
+    np.testing.assert_allclose(res.s[live], s_ref[live], rtol=1e-10)
+    np.testing.assert_allclose(res.U[:, live], g["U_brain"][:, live], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res.V[:, live], g["V_design"][:, live], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res.X_latent[:, live], g["X_latent"][:, live], rtol=1e-8, atol=1e-9)
+    for f in ("lvcorrs", "lvintercorrs", "R", "X_mc", "X_means", "multiblock", "Y_latent", "Tusc", "Busc",
+              "Tvsc", "Bvsc", "Tv", "Bv"):
+        if f in g:
+            a, b = np.asarray(getattr(res, f)), g[f]
+            assert a.shape == b.shape, f
+            if a.shape[-1] == live.size and f not in ("R", "X_mc", "X_means", "multiblock"):
+                a, b = a[..., live], b[..., live]
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-9, err_msg=f)
+    assert res.resample_tests.permute_ratio == "NA" and res.resample_tests.boot_ratios == "NA"
+    assert res.resample_tests.conf_ints == ["NA", "NA"]
+
+
+def test_argument_validation_matches_reference():
+    import plspy_b200
+    from plspy_b200 import exceptions
+    X = np.random.RandomState(0).standard_normal((12, 10))
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=-1, num_boot=0)
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=1.5)
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, num_split=-2)
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, num_split=2, lv=0)
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, num_split=2, lv=1, CI=1.5)
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, pls_method="nope")
+    with pytest.raises(ValueError):
+        plspy_b200.PLS(X, (2, 2), 3, Y=X, num_perm=0, num_boot=0)                      # Y given to mct
+    with pytest.raises(exceptions.InputMatrixDimensionMismatchError):
+        plspy_b200.PLS(X, (2, 3), 3, num_perm=0, num_boot=0)
+    with pytest.raises(exceptions.ImproperShapeError):
+        plspy_b200.PLS(X[0], (2, 2), 3, num_perm=0, num_boot=0)
+    with pytest.raises(exceptions.MissingParameterError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, pls_method="rb")
+    with pytest.raises(exceptions.MissingParameterError):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=0, num_boot=0, pls_method="cst")
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import plspy_b200
+    X = np.random.RandomState(0).standard_normal((12, 10))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        plspy_b200.PLS(X, (2, 2), 3, num_perm=5, num_boot=0)
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "plspy_b200")
+    for f in os.listdir(root):
+        if f.endswith(".py"):
+            src = open(os.path.join(root, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
