@@ -283,7 +283,7 @@ def run_gpu(args):
     except Exception:  # noqa: BLE001
         pass
     roofline = {
-        "kernel": "boot_moments_kernel<80,3> (FP64 DMMA.8x8x4)", "bound": "tensor", "achieved": achieved, "peak": peak,
+        "kernel": "boot_moments_kernel<76,3> (FP64 DMMA.8x8x4, A-fragments register-resident, TMA-bulk-fed B)", "bound": "tensor", "achieved": achieved, "peak": peak,
         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/FP64_PEAKS.json); "
                        "MEASURED_PEAKS.json carries no FP64 figure",

@@ -59,8 +59,8 @@ static bool boot_plan(int N, int K, int R, int64_t p, BootPlan& b) {
     if (!best_kp) return false;
     b.Kp = best_kp; b.nblk = best_blk; b.nb = 8 * best_blk / best_kp;
     b.nks = (int)cdiv(N, 16) * 4;
-    if (b.nks <= 20) b.maxks = 20; else if (b.nks <= 40) b.maxks = 40; else if (b.nks <= 60) b.maxks = 60;
-    else if (b.nks <= 80) b.maxks = 80; else return false;
+    if (b.nks > 80) return false;
+    b.maxks = b.nks;
     b.nper = (int)cdiv(R, b.nb);
     b.stage_doubles = (size_t)b.nks * b.nblk * 32;
     const size_t red = (size_t)BM_WARPS * 8 * b.Kp * 2 * sizeof(double);
@@ -126,14 +126,18 @@ __global__ void __launch_bounds__(256) boot_coef_pack_kernel(const double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int MAXKS, int NBLK>
+// NKS (k-steps of 4 rows) is a compile-time constant so that the whole period is one straight-line
+// stream of NKS*NBLK {LDS.64, DMMA} pairs that ptxas can software-pipeline; kernels are instantiated
+// for every multiple of 4 up to 80 (N <= 320).
+template <int NKS, int NBLK>
 __global__ void __launch_bounds__(BM_THREADS, 1)
 boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
-                    const double* __restrict__ coef, int nks, int nper, int per_per_split, int nstage,
+                    const double* __restrict__ coef, int nper, int per_per_split, int nstage,
                     int R, int Kp, int K, const double* __restrict__ pivot,
                     double* __restrict__ osum, double* __restrict__ osumsq) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int stage_doubles = nks * NBLK * 32;
+    constexpr int stage_doubles = NKS * NBLK * 32;
+    constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
     double* ring = reinterpret_cast<double*>(smraw);
     double* red = ring + (size_t)nstage * stage_doubles;              // [8 warps][2][8][Kp]
     uint64_t* full = reinterpret_cast<uint64_t*>(red + BM_WARPS * 16 * Kp);
@@ -145,7 +149,6 @@ boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long lon
     const int per0 = blockIdx.y * per_per_split;
     const int per1 = min(nper, per0 + per_per_split);
     const int nit = per1 - per0;
-    const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
 
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, BM_WARPS); }
@@ -153,84 +156,98 @@ boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long lon
     }
     __syncthreads();
 
-    auto issue = [&](int it) {   // thread 0 only: stream period per0+it into slot it % nstage
-        const int slot = it % nstage;
+    auto issue = [&](int it, int slot) {   // thread 0 only: stream period per0+it into `slot`
         mbar_expect_tx(full + slot, stage_bytes);
         const char* src = reinterpret_cast<const char*>(coef + (size_t)(per0 + it) * stage_doubles);
         char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+#pragma unroll 1
         for (uint32_t off = 0; off < stage_bytes; off += 16384u) {
             const uint32_t n = min(16384u, stage_bytes - off);
             bulk_g2s(dst + off, src + off, n, full + slot);
         }
     };
     if (tid == 0)
-        for (int it = 0; it < min(nstage, nit); ++it) issue(it);
+        for (int it = 0; it < min(nstage, nit); ++it) issue(it, it);
 
     // ---- A fragments: this warp's 8 voxels x all rows, resident in registers
-    double a[MAXKS];
+    double a[NKS];
 #pragma unroll
-    for (int s = 0; s < MAXKS; ++s) {
+    for (int s = 0; s < NKS; ++s) {
         const int row = 4 * s + q;
-        a[s] = (s < nks && row < N && v < p) ? __ldg(X + (long long)row * ldx + v) : 0.0;
+        a[s] = (row < N && v < p) ? __ldg(X + (long long)row * ldx + v) : 0.0;
     }
 
     // ---- per-thread column bookkeeping (fixed for the whole kernel)
-    int kk[NBLK][2], bo[NBLK][2];
     double piv[NBLK][2], s1[NBLK][2], s2[NBLK][2];
 #pragma unroll
     for (int j = 0; j < NBLK; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int c = 8 * j + 2 * q + e;
-            kk[j][e] = c % Kp; bo[j][e] = c / Kp;
-            piv[j][e] = (pivot != nullptr && kk[j][e] < K && v < p) ? __ldg(pivot + v * K + kk[j][e]) : 0.0;
+            const int c = 8 * j + 2 * q + e, k = c % Kp;
+            piv[j][e] = (pivot != nullptr && k < K && v < p) ? __ldg(pivot + v * K + k) : 0.0;
             s1[j][e] = 0.0; s2[j][e] = 0.0;
         }
     const int nb = 8 * NBLK / Kp;
 
+    // The two warps that share an SM sub-partition (w and w+4) run half a period apart, so that one of
+    // them always has a full MMA stream in flight while the other folds its accumulators and waits on
+    // the next stage (otherwise all eight warps drain the DMMA pipe at the same instant).
+    if (warp >= 4) __nanosleep((unsigned)(NKS * NBLK * 8));
+
+    int slot = 0, prev_slot = 0;
+    uint32_t phase = 0, prev_phase = 0;
     for (int it = 0; it < nit; ++it) {
-        const int slot = it % nstage;
         if (tid == 0 && it > 0) {
             // refill the slot drained in the previous iteration with period it-1+nstage
             const int nx = it - 1 + nstage;
             if (nx < nit) {
-                mbar_wait(empty + (it - 1) % nstage, ((it - 1) / nstage) & 1);
-                issue(nx);
+                mbar_wait(empty + prev_slot, prev_phase);
+                issue(nx, prev_slot);
             }
         }
         __syncwarp();
-        mbar_wait(full + slot, (it / nstage) & 1);
+        mbar_wait(full + slot, phase);
 
         double d[NBLK][2];
 #pragma unroll
         for (int j = 0; j < NBLK; ++j) { d[j][0] = -piv[j][0]; d[j][1] = -piv[j][1]; }
-        const double* bs = ring + (size_t)slot * stage_doubles + lane;
+        // volatile: ptxas must keep these loads in program order (s-major, chains round-robin), which
+        // keeps the NBLK accumulator chains interleaved; without it the straight-line stream is
+        // re-ordered chain by chain (fewest live registers) and every DMMA waits on its predecessor.
+        const volatile double* bs = ring + (size_t)slot * stage_doubles + lane;
 #pragma unroll
-        for (int s0 = 0; s0 < MAXKS; s0 += 4) {
-            if (s0 < nks) {
+        for (int s = 0; s < NKS; ++s) {
 #pragma unroll
-                for (int s = s0; s < s0 + 4; ++s) {
-#pragma unroll
-                    for (int j = 0; j < NBLK; ++j) {
-                        const double b = bs[(s * NBLK + j) * 32];
-                        dmma884(d[j][0], d[j][1], a[s], b);
-                    }
-                }
+            for (int j = 0; j < NBLK; ++j) {
+                const double b = bs[(s * NBLK + j) * 32];
+                dmma884(d[j][0], d[j][1], a[s], b);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
 
-        const int rbase = (per0 + it) * nb;
+        if (it + 1 < nit || (per0 + it + 1) * nb <= R) {      // every slot of the period is a real resample
 #pragma unroll
-        for (int j = 0; j < NBLK; ++j)
+            for (int j = 0; j < NBLK; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (rbase + bo[j][e] < R) {
+                for (int e = 0; e < 2; ++e) {
                     s1[j][e] += d[j][e];
                     s2[j][e] = fma(d[j][e], d[j][e], s2[j][e]);
                 }
-            }
+        } else {                                              // ragged last period: mask the padding slots
+            const int rbase = (per0 + it) * nb;
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (rbase + (8 * j + 2 * q + e) / Kp < R) {
+                        s1[j][e] += d[j][e];
+                        s2[j][e] = fma(d[j][e], d[j][e], s2[j][e]);
+                    }
+                }
+        }
+        prev_slot = slot; prev_phase = phase;
+        if (++slot == nstage) { slot = 0; phase ^= 1u; }
     }
 
     // ---- fold the nb resample slots of a period onto k, in slot order (deterministic)
@@ -242,11 +259,13 @@ boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long lon
 #pragma unroll
         for (int j = 0; j < NBLK; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (bo[j][e] == round) {
-                    r1[vr * Kp + kk[j][e]] += s1[j][e];
-                    r2[vr * Kp + kk[j][e]] += s2[j][e];
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * j + 2 * q + e;
+                if (c / Kp == round) {
+                    r1[vr * Kp + c % Kp] += s1[j][e];
+                    r2[vr * Kp + c % Kp] += s2[j][e];
                 }
+            }
         __syncwarp();
     }
     const long long vbase = (long long)blockIdx.x * BM_VOX + warp * 8;
@@ -357,25 +376,30 @@ __global__ void xv_reduce_kernel(const double* __restrict__ part, int nchunk, in
     out[i] = s;
 }
 
-template <int MAXKS, int NBLK>
+template <int NKS, int NBLK>
 static int launch_moments(const BootPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
                           int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_kernel<MAXKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_kernel<NKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)b.smem_bytes));
     dim3 grid((unsigned)cdiv(p, BM_VOX), (unsigned)b.nsplit);
-    boot_moments_kernel<MAXKS, NBLK><<<grid, BM_THREADS, b.smem_bytes, st>>>(
-        X, ldx, N, p, coef, b.nks, b.nper, b.per_per_split, b.nstage, R, b.Kp, K, pivot, o1, o2);
+    boot_moments_kernel<NKS, NBLK><<<grid, BM_THREADS, b.smem_bytes, st>>>(
+        X, ldx, N, p, coef, b.nper, b.per_per_split, b.nstage, R, b.Kp, K, pivot, o1, o2);
     PLSB_LAUNCH_CHECK("boot_moments_kernel");
     return PLSB200_OK;
 }
 
-template <int MAXKS>
-static int dispatch_nblk(const BootPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
-                         int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
-    switch (b.nblk) {
-        case 1: return launch_moments<MAXKS, 1>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        case 2: return launch_moments<MAXKS, 2>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        default: return launch_moments<MAXKS, 3>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+template <int NBLK>
+static int dispatch_nks(const BootPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                        int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    switch (b.nks) {
+#define PLSB_CASE(n) case n: return launch_moments<n, NBLK>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        PLSB_CASE(4) PLSB_CASE(8) PLSB_CASE(12) PLSB_CASE(16) PLSB_CASE(20) PLSB_CASE(24) PLSB_CASE(28)
+        PLSB_CASE(32) PLSB_CASE(36) PLSB_CASE(40) PLSB_CASE(44) PLSB_CASE(48) PLSB_CASE(52) PLSB_CASE(56)
+        PLSB_CASE(60) PLSB_CASE(64) PLSB_CASE(68) PLSB_CASE(72) PLSB_CASE(76) PLSB_CASE(80)
+#undef PLSB_CASE
+        default:
+            set_err("boot_moments_f64: no kernel for nks=%d", b.nks);
+            return PLSB200_EUNSUPPORTED;
     }
 }
 
@@ -434,11 +458,10 @@ extern "C" int plsb200_boot_moments_f64(const double* X, int N, int64_t p, int64
         o2 = o1 + (size_t)b.nsplit * p * K;
     }
     int rc;
-    switch (b.maxks) {
-        case 20: rc = dispatch_nblk<20>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
-        case 40: rc = dispatch_nblk<40>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
-        case 60: rc = dispatch_nblk<60>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
-        default: rc = dispatch_nblk<80>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+    switch (b.nblk) {
+        case 1: rc = dispatch_nks<1>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+        case 2: rc = dispatch_nks<2>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
+        default: rc = dispatch_nks<3>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st); break;
     }
     if (rc != PLSB200_OK) return rc;
     if (b.nsplit > 1) {
