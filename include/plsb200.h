@@ -124,6 +124,36 @@ int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* str
 int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
                          const int32_t* idx, int R, double* VS, void* stream);
 
+/* ---- K3: batched symmetric eigensolver, one warp per K x K matrix (K <= 32), one-sided Jacobi with
+ * shuffle-based rotations.  Replaces np.linalg.svd of the K x p half-sample cross-block matrices
+ * (class_functions.py:122 as called from split_half_resampling.py:194,207,255,311,612-613,...) through
+ * their K x K Gram matrices.  A: B x K x K symmetric PSD.  evals: B x K descending.
+ * evecs: B x K x K row-major, eigenvectors in COLUMNS.                                              */
+int plsb200_sym_eig_f64(const double* A, int K, int B, double* evals, double* evecs, void* stream);
+
+/* ---- Gram blocks of S split-half resamples through G (task methods).
+ * Half h of split s consists of the rows idx_h[s, 0..n_h) of X (null splits: rows of the permuted X,
+ * i.e. composed indices); its cross-block matrix is M_h = A_h (K x n_h) . X[idx_h].  Outputs
+ * S11 = M1 M1^T, S12 = M1 M2^T, S22 = M2 M2^T, each S x K x K.
+ * (split_half_resampling.py:172-196, 289-313, 590-613, 709-732)                                    */
+int plsb200_split_gram_f64(const double* G, int N, const int32_t* idx1, int n1, const int32_t* idx2, int n2,
+                           int S, const double* A1, const double* A2, int K, double* S11, double* S12,
+                           double* S22, void* stream);
+
+/* ---- split-half outputs from the Gram blocks (SVD methods; K <= 32).  With S11 = U1 diag(s1^2) U1^T,
+ * S22 = U2 diag(s2^2) U2^T (singular values descending):
+ *   s_train (S x K)     = s1                                   (split_half_resampling.py:195)
+ *   s_test  (S x K x K) = V1^T M2^T U1 = diag(1/s1) U1^T S12 U1 (:196)
+ *   u_repro (S x K x K) = V1^T V2 = diag(1/s1) U1^T S12 U2 diag(1/s2)   (:682)
+ *   v_repro (S x K x K) = U1^T U2                              (:683)
+ *   s2      (S x K)     = s2
+ * Any output pointer may be NULL.  Rows/columns belonging to zero singular values are written as 0
+ * (LAPACK returns an arbitrary orthonormal completion there).  Signs of singular vectors are not
+ * those of LAPACK: compare up to the sign of each latent variable.                                 */
+int plsb200_split_svd_f64(const double* S11, const double* S12, const double* S22, int K, int S,
+                          double* s_train, double* s_test, double* u_repro, double* v_repro, double* s2,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

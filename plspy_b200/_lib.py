@@ -55,6 +55,11 @@ SIGNATURES = {
     "plsb200_boot_finalize_f64": (c_int, [c_double_p, c_double_p, c_int64, c_int, c_int64, c_double_p,
                                           c_double_p, c_double_p, c_void_p]),
     "plsb200_colstd_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_void_p]),
+    "plsb200_sym_eig_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_void_p]),
+    "plsb200_split_gram_f64": (c_int, [c_double_p, c_int, c_int32_p, c_int, c_int32_p, c_int, c_int, c_double_p,
+                                       c_double_p, c_int, c_double_p, c_double_p, c_double_p, c_void_p]),
+    "plsb200_split_svd_f64": (c_int, [c_double_p, c_double_p, c_double_p, c_int, c_int, c_double_p, c_double_p,
+                                      c_double_p, c_double_p, c_double_p, c_void_p]),
     "plsb200_salience_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,
                                      c_double_p, c_void_p]),
 }

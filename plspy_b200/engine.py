@@ -206,3 +206,37 @@ class Engine:
             check(lib.plsb200_salience_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(E), K, self._p(idx), R,
                                            self._p(out), self._stream()), "salience_f64")
         return out
+
+    # ------------------------------------------------------------------ split-half (K3)
+    def sym_eig(self, A):
+        """Batched symmetric eigendecomposition (B x K x K, K <= 32): evals descending, evecs in columns."""
+        A = self.to_device(A, F64)
+        B, K = int(A.shape[0]), int(A.shape[1])
+        ev = self._empty(B, K); U = self._empty(B, K, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_sym_eig_f64(self._p(A), K, B, self._p(ev), self._p(U), self._stream()), "sym_eig_f64")
+        return ev, U
+
+    def split_gram(self, idx1, idx2, A1, A2):
+        """S11, S12, S22 (S x K x K) of the half-sample cross-block matrices M_h = A_h X[idx_h]."""
+        idx1 = self.to_device(idx1, I32); idx2 = self.to_device(idx2, I32)
+        A1 = self.to_device(A1, F64); A2 = self.to_device(A2, F64)
+        S, n1, n2, K = int(idx1.shape[0]), int(idx1.shape[1]), int(idx2.shape[1]), int(A1.shape[0])
+        assert A1.shape[1] == n1 and A2.shape == (K, n2) and idx2.shape[0] == S
+        out = [self._empty(S, K, K) for _ in range(3)]
+        G = self.G
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_split_gram_f64(self._p(G), self.N, self._p(idx1), n1, self._p(idx2), n2, S, self._p(A1),
+                                             self._p(A2), K, self._p(out[0]), self._p(out[1]), self._p(out[2]),
+                                             self._stream()), "split_gram_f64")
+        return out
+
+    def split_svd(self, S11, S12, S22):
+        """(s_train, s_test, u_repro, v_repro, s2) from the Gram blocks (see include/plsb200.h)."""
+        S, K = int(S11.shape[0]), int(S11.shape[1])
+        s1 = self._empty(S, K); s2 = self._empty(S, K)
+        st = self._empty(S, K, K); ur = self._empty(S, K, K); vr = self._empty(S, K, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_split_svd_f64(self._p(S11), self._p(S12), self._p(S22), K, S, self._p(s1), self._p(st),
+                                            self._p(ur), self._p(vr), self._p(s2), self._stream()), "split_svd_f64")
+        return s1, st, ur, vr, s2

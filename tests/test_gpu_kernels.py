@@ -171,3 +171,54 @@ def test_error_reporting(torch_cuda):
     eng = Engine(np.zeros((400, 10)))
     with pytest.raises(PlsB200Error):
         eng.boot_moments(np.zeros((400, 3)), np.zeros((2, 400), np.int32))   # N > 320 not supported yet
+
+
+@pytest.mark.parametrize("K", [3, 6, 12, 16, 24, 32])
+def test_sym_eig_jacobi(torch_cuda, K):
+    """K3: warp-per-matrix one-sided Jacobi vs LAPACK (np.linalg.eigh) on PSD Gram matrices,
+    including rank-deficient ones.  North-star tolerance: singular values 1e-10 relative."""
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(K)
+    B = 37
+    A = np.empty((B, K, K))
+    for b in range(B):
+        M = rs.standard_normal((K, 3 * K)) * np.logspace(0, -3, K)[:, None]
+        if b % 5 == 0:
+            M[-1] = M[0]                     # exact rank deficiency
+        A[b] = M @ M.T
+    eng = Engine(np.zeros((2, 2)))
+    ev, U = eng.sym_eig(A)
+    ev = ev.cpu().numpy(); U = U.cpu().numpy()
+    for b in range(B):
+        w = np.linalg.eigvalsh(A[b])[::-1]
+        np.testing.assert_allclose(ev[b], w, rtol=1e-10, atol=1e-12 * w[0])
+        np.testing.assert_allclose(U[b].T @ U[b], np.eye(K), atol=1e-12)               # orthonormal
+        np.testing.assert_allclose(U[b] @ np.diag(ev[b]) @ U[b].T, A[b], atol=1e-11 * w[0])
+        s_ref = np.linalg.svd(np.linalg.cholesky(A[b] + 1e-300 * np.eye(K)) if False else A[b], compute_uv=False)
+        np.testing.assert_allclose(np.sqrt(ev[b][:K // 2]), np.sqrt(s_ref[:K // 2]), rtol=1e-10)
+
+
+def test_split_gram_and_svd(torch_cuda):
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(21)
+    N, p, K, S, n1, n2 = 40, 500, 6, 9, 18, 22
+    X = rs.standard_normal((N, p))
+    A1 = rs.standard_normal((K, n1)); A2 = rs.standard_normal((K, n2))
+    i1 = np.array([rs.permutation(N)[:n1] for _ in range(S)], dtype=np.int32)
+    i2 = np.array([rs.permutation(N)[:n2] for _ in range(S)], dtype=np.int32)
+    eng = Engine(X)
+    S11, S12, S22 = eng.split_gram(i1, i2, A1, A2)
+    s1, st, ur, vr, s2 = [t.cpu().numpy() for t in eng.split_svd(S11, S12, S22)]
+    for s in range(S):
+        M1 = A1 @ X[i1[s]]; M2 = A2 @ X[i2[s]]
+        np.testing.assert_allclose(S11[s].cpu().numpy(), M1 @ M1.T, rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(S12[s].cpu().numpy(), M1 @ M2.T, rtol=1e-11, atol=1e-9)
+        U1, sv1, V1t = np.linalg.svd(M1, full_matrices=False)
+        U2, sv2, V2t = np.linalg.svd(M2, full_matrices=False)
+        np.testing.assert_allclose(s1[s], sv1, rtol=1e-10)
+        np.testing.assert_allclose(s2[s], sv2, rtol=1e-10)
+        test = V1t @ M2.T @ U1
+        np.testing.assert_allclose(np.abs(st[s]), np.abs(test), rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(np.diag(st[s]), np.diag(test), rtol=1e-8, atol=1e-9)      # diagonal is sign-free
+        np.testing.assert_allclose(np.abs(ur[s]), np.abs(V1t @ V2t.T), rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(np.abs(vr[s]), np.abs(U1.T @ U2), rtol=1e-8, atol=1e-9)

@@ -121,3 +121,37 @@ def test_unimplemented_methods_fail_loudly():
     g = _load("rb_bal")
     with pytest.raises(plspy_b200.exceptions.NotImplementedError):
         _run_product(g)
+
+
+SPLIT_CASES = [c for c in TASK_CASES if int(_load(c)["nsplit"]) > 0]
+
+
+@pytest.mark.parametrize("name", SPLIT_CASES)
+def test_split_half_matches_reference_golden(name):
+    """Full PLS(...) with num_split: the RNG stream after perms/boots must line up with the reference's,
+    and every split-half output must match (singular-vector signs are LAPACK's in the reference:
+    off-diagonals and cosine cubes are compared in absolute value, like the reference's own metrics)."""
+    g = _load(name)
+    res = _run_product(g, num_split=int(g["nsplit"]), lv=int(g["lv"]))
+    tt, sh = res.pls_repro_tt, res.pls_repro_sh
+    lvn = int(g["lv"])
+    live = np.abs(g["s"]) > 1e-8
+    nl = int(live.sum()) if str(g["method"]) == "mct" else g["tt_pls_s_train"].shape[0]
+    for k in ("pls_s_train", "pls_s_test", "pls_s_train_null", "pls_s_test_null"):
+        a, b = tt[k], g["tt_" + k]
+        assert a.shape == b.shape, k
+        if "train" in k:
+            np.testing.assert_allclose(a[:, :nl - 1, :], b[:, :nl - 1, :], rtol=1e-9, atol=1e-10, err_msg=k)
+        else:
+            d = np.arange(nl - 1)
+            np.testing.assert_allclose(a[d, d, :], b[d, d, :], rtol=1e-7, atol=1e-9, err_msg=k)
+            np.testing.assert_allclose(np.abs(a[:nl - 1, :nl - 1]), np.abs(b[:nl - 1, :nl - 1]), rtol=1e-7, atol=1e-8, err_msg=k)
+    np.testing.assert_allclose(np.asarray(tt["z"])[:lvn], g["tt_z"][:lvn], rtol=1e-7)
+    np.testing.assert_allclose(np.asarray(tt["z_null"])[:lvn], g["tt_z_null"][:lvn], rtol=1e-7)
+    for k in ("pls_dist_u", "pls_dist_v", "pls_dist_null_u", "pls_dist_null_v"):
+        a, b = sh[k], g["sh_" + k]
+        assert a.shape == b.shape, k
+        np.testing.assert_allclose(np.abs(a[:nl - 1, :nl - 1]), np.abs(b[:nl - 1, :nl - 1]), rtol=1e-7, atol=1e-8, err_msg=k)
+    for k in g:
+        if k.startswith("sh_pls_") and "dist" not in k:
+            np.testing.assert_allclose(np.asarray(sh[k[3:]]), g[k], rtol=1e-7, atol=1e-9, err_msg=k)
