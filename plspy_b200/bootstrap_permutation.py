@@ -185,8 +185,8 @@ class _ResampleTestPLS(ResampleTest):
         counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg == "mct" else 0.0)
         dist.allreduce_sum_(counts)
         s_hat = dist.gather_rows(s_hat, niter, lo)
-        counts = counts.cpu().numpy().astype(float)
-        s_list = s_hat.cpu().numpy()
+        counts, s_list = eng.to_host(counts, s_hat)
+        counts = counts.astype(float)
         permute_ratio = counts[:K] / (niter + 1)
         stepdown_ratio = counts[K:] / (niter + 1)
         _log(f"real s: {s}\nratio: {permute_ratio}\nStepdown perm ratio: {stepdown_ratio}")
@@ -238,13 +238,15 @@ class _ResampleTestPLS(ResampleTest):
         if left is not None:
             left = dist.gather_rows(left, niter, lo)
         z = norm.ppf(1 - (1 - CI) / 2)                                      # (:709)
-        half = eng.colstd(Tdist).cpu().numpy() * z                          # (:715-716)
+        std_T, std_errs_h, boot_ratios_h, Tdist_h, left_h = eng.to_host(
+            eng.colstd(Tdist), std_errs, boot_ratios, Tdist, left)
+        half = std_T * z                                                    # (:715-716)
         conf_int = (Tvsc_orig - half, Tvsc_orig + half)
 
         debug = _LazyDebugDict()
-        debug["left_sv_sampled"] = (left.cpu().numpy() if left is not None
+        debug["left_sv_sampled"] = (left_h if left_h is not None
                                     else np.zeros((niter, Ucoef.shape[0], Ucoef.shape[1])))
-        debug["Tdistrib"] = Tdist.cpu().numpy()
+        debug["Tdistrib"] = Tdist_h
         debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
 
         def _right():   # the reference's B x p x K cube, only on request
@@ -254,7 +256,7 @@ class _ResampleTestPLS(ResampleTest):
                                   "accumulates its moments on the fly instead of storing it")
             return eng.salience(E, _index_shard(eng, indices, niter, 0, niter)).cpu().numpy()
         debug.set_lazy("right_sv_sampled", _right)
-        return conf_int, std_errs.cpu().numpy(), boot_ratios.cpu().numpy(), debug
+        return conf_int, std_errs_h, boot_ratios_h, debug
 
     # ------------------------------------------------------------------------------------------
     def __repr__(self):

@@ -135,16 +135,40 @@ __global__ void uhat_kernel(const double* __restrict__ XL, int N, int K, const d
     }
 }
 
-// population std over axis 0 of A[R][M]; two-pass like numpy (mean, then mean of squared deviations)
-__global__ void colstd_kernel(const double* __restrict__ A, int R, long long M, double* __restrict__ out) {
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
+// population std over axis 0 of A[R][M], two-pass like numpy (mean, then mean of squared deviations).
+// One warp per column strip of 32 columns x all rows would serialise R loads; instead a CTA owns 32
+// columns, its 8 warps stride over the rows (coalesced 256-B row segments) and the per-warp partials
+// are combined in a fixed order through shared memory (deterministic).
+__global__ void __launch_bounds__(256) colstd_kernel(const double* __restrict__ A, int R, long long M,
+                                                    double* __restrict__ out) {
+    __shared__ double part[8][33];
+    __shared__ double mean[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long m = (long long)blockIdx.x * 32 + lane;
+    const bool ok = m < M;
     double s = 0.0;
-    for (int r = 0; r < R; ++r) s += A[(size_t)r * M + m];
-    const double mu = s / R;
+    for (int r = warp; r < R; r += 8) s += ok ? A[(size_t)r * M + m] : 0.0;
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        mean[lane] = t / R;
+    }
+    __syncthreads();
+    const double mu = mean[lane];
     double q = 0.0;
-    for (int r = 0; r < R; ++r) { const double d = A[(size_t)r * M + m] - mu; q = fma(d, d, q); }
-    out[m] = sqrt(q / R);
+    for (int r = warp; r < R; r += 8) {
+        const double d = ok ? A[(size_t)r * M + m] - mu : 0.0;
+        q = fma(d, d, q);
+    }
+    part[warp][lane] = q;
+    __syncthreads();
+    if (warp == 0 && ok) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        out[m] = sqrt(t / R);
+    }
 }
 
 template <int KT>
@@ -224,7 +248,7 @@ extern "C" int plsb200_uhat_f64(const double* XL, int N, int K, const double* Lo
 extern "C" int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* stream) {
     PLSB_CHECK_ARG(A && out, "colstd_f64: null pointer");
     PLSB_CHECK_ARG(R > 0 && M > 0, "colstd_f64: bad shape");
-    colstd_kernel<<<(int)cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(A, R, M, out);
+    colstd_kernel<<<(int)cdiv(M, 32), 256, 0, (cudaStream_t)stream>>>(A, R, M, out);
     PLSB_LAUNCH_CHECK("colstd_kernel");
     return PLSB200_OK;
 }

@@ -47,10 +47,20 @@ def allreduce_packed_(tensors):
 
 def gather_rows(local, n_total, lo):
     """Assemble per-resample rows computed on each rank's shard into the full [n_total, ...] tensor on
-    every rank: each rank writes its rows into a zero tensor and the ranks are summed (exact: every
-    element has exactly one non-zero contribution)."""
-    if world()[1] == 1:
+    every rank with ONE all_gather (shards padded to the largest shard, then trimmed)."""
+    import torch.distributed as dist
+    rank, size = world()
+    if size == 1:
         return local
-    full = torch.zeros((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    full[lo:lo + local.shape[0]] = local
-    return allreduce_sum_(full)
+    spans = [shard(n_total, r, size) for r in range(size)]
+    mx = max(hi - l for l, hi in spans)
+    tail = tuple(local.shape[1:])
+    buf = local
+    if local.shape[0] != mx:
+        buf = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+        buf[:local.shape[0]] = local
+    out = torch.empty((size * mx,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf.contiguous())
+    if all(hi - l == mx for l, hi in spans):
+        return out
+    return torch.cat([out[r * mx:r * mx + (hi - l)] for r, (l, hi) in enumerate(spans)], dim=0)

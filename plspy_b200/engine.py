@@ -58,6 +58,21 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def to_host(self, *tensors):
+        """Device -> host through pinned staging buffers (torch's caching host allocator), one
+        synchronisation for the whole batch; returns numpy arrays (None passes through)."""
+        staged = []
+        for t in tensors:
+            if t is None:
+                staged.append(None)
+                continue
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            staged.append(h)
+        torch.cuda.current_stream(self.device).synchronize()
+        out = [None if h is None else h.numpy() for h in staged]
+        return out[0] if len(out) == 1 else out
+
     def _empty(self, *shape, dtype=F64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
