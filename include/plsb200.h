@@ -124,6 +124,38 @@ int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* str
 int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
                          const int32_t* idx, int R, double* VS, void* stream);
 
+/* ---- K5: behaviour PLS (rb / csb) -----------------------------------------------------------------
+ * Cells = (group, condition) blocks of consecutive rows, given as ncell+1 int32 offsets `cell_start`.
+ *
+ * cell_standardize: Xc = X - block means, Z = Xc / (block sd * sqrt(n)) (0 where sd == 0): the X half of
+ *   `_compute_corr` (class_functions.py:221-238), done once per analysis.  Xc, Z: N x p dense (Z may be NULL).
+ * nspace_coef: like plsb200_nspace_f64 but with an explicit coefficient matrix per resample
+ *   (C: R x N x K): d2[r,k] = C_r[:,k]^T G C_r[:,k].  With G = Z Z^T this is the permuted behaviour PLS
+ *   singular-value estimate (bootstrap_permutation.py:395-405, 429-437; only Y is permuted).
+ * rb_coef: per resample, Ynew = Y[idx] (idx may be NULL = identity), z-scored inside every block;
+ *   Q[r] (N x Kc) = pull-back of the design weights U (ncell*nb x Kc) to row space;
+ *   scatter = 0: permutation (X rows stay), scatter = 1: bootstrap (X rows gathered by the same idx;
+ *   W[r] (N) = multiplicity / block size).  Yz (R x N x nb, optional) = the z-scored resampled Y.
+ * rb_boot: the p-space bootstrap pass for bootstraps [b0, b0+nbt): VS_b = R_b^T U with the per-voxel
+ *   block std of the RESAMPLED rows (class_functions.py:219-245 as called at bootstrap_permutation.py:613);
+ *   accumulates sum/sumsq of (VS - pivot) INTO sum/sumsq (p x K, caller zeroes before the first chunk) and
+ *   writes T[b] = Xc . VS_b (N x K) and nrm2[b] = ||VS_b[:,k]||^2 for the LV correlations.
+ * rb_lvcorr: LVcorr[b] = _compute_corr(X_new @ V_hat, Y_new) (ncell*nb x K)  (bootstrap_permutation.py:636-642). */
+int plsb200_cell_standardize_f64(const double* X, int N, int64_t p, int64_t ldx, const int32_t* cell_start,
+                                 int ncell, double* Xc, double* Z, void* stream);
+int plsb200_nspace_coef_f64(const double* G, int N, const double* C, int K, int R, const double* Lmat, int Kt,
+                            double* d2, double* T, void* stream);
+int plsb200_rb_coef_f64(const double* Y, int N, int nb, const int32_t* idx, int R, const int32_t* cell_start,
+                        int ncell, const double* U, int Kc, int scatter, double* Q, double* W, double* Yz,
+                        void* stream);
+size_t plsb200_rb_boot_f64_workspace(int N, int64_t p, int K, int nbt);
+int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
+                        int nbt, const int32_t* cell_start, int ncell, const double* pivot, double* sum,
+                        double* sumsq, double* T, double* nrm2, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int plsb200_rb_lvcorr_f64(const double* T, const double* nrm2, const double* Yz, const int32_t* idx, int N, int nb,
+                          int K, int R, const int32_t* cell_start, int ncell, double* LVcorr, void* stream);
+
 /* ---- K3: batched symmetric eigensolver, one warp per K x K matrix (K <= 32), one-sided Jacobi with
  * shuffle-based rotations.  Replaces np.linalg.svd of the K x p half-sample cross-block matrices
  * (class_functions.py:122 as called from split_half_resampling.py:194,207,255,311,612-613,...) through

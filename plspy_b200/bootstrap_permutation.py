@@ -108,6 +108,24 @@ def _indices_to_host(indices, niter):
     return np.asarray(indices)[:niter]
 
 
+def _cell_offsets(cond_order):
+    """int32 offsets of the (group, condition) blocks of rows."""
+    sizes = np.asarray(cond_order).reshape(-1)
+    return np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+
+
+def _behaviour_state(eng, cells):
+    """Per-engine cache of the block-centred X, its z-scored copy's Gram matrix (Gz = Z Z^T)."""
+    st = getattr(eng, "_behaviour", None)
+    key = tuple(int(c) for c in cells)
+    if st is None or st["key"] != key:
+        Xc, Z = eng.cell_standardize(cells)
+        st = {"key": key, "Xc": Xc, "Gz": eng.gram_of(Z)}
+        del Z
+        eng._behaviour = st
+    return st
+
+
 def _task_operators(pls_alg, cond_order, mctype, U, contrast):
     """Row-space pull-back of the design-side weights: E = Lop^T @ Ucoef (N x K).
     mct: Lop = centring operator, Ucoef = U (bootstrap_permutation.py:385-387, 404);
@@ -135,7 +153,7 @@ class _ResampleTestPLS(ResampleTest):
                  CI=0.95, *, perm_indices=None, boot_indices=None, engine=None):
         self.CI = CI
         _log(f"PLS ALG: {self.pls_alg}")
-        if self.pls_alg not in ("mct", "cst") and (nperm > 0 or nboot > 0):
+        if self.pls_alg in ("mb", "cmb") and (nperm > 0 or nboot > 0):
             raise exceptions.NotImplementedError(
                 f"{self._pls_types.get(self.pls_alg, self.pls_alg)}: permutation/bootstrap tests are not yet "
                 "available on the B200 path (no CPU fallback is provided).")
@@ -174,15 +192,29 @@ class _ResampleTestPLS(ResampleTest):
         s[np.abs(s) < threshold] = 0
         org_s = np.copy(s)
         totcov_org = _stepdown_tail(org_s)
+        behaviour = pls_alg in ("rb", "csb")
         if indices is None:
-            indices = resample.permutation_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)[0]
-        Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
-        K = E.shape[1]
-
+            indices = resample.permutation_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)
+        if isinstance(indices, tuple):
+            indices = indices[1] if behaviour else indices[0]
         lo, hi = dist.shard(niter)
         idx_dev = _index_shard(eng, indices, niter, lo, hi)
-        d2, _ = eng.nspace(E, idx_dev)
-        counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg == "mct" else 0.0)
+        if behaviour:
+            # only Y is permuted (:337-340, 395-396): X keeps its block z-scores, so everything lives in
+            # N-space through Gz = Z Z^T
+            cells = _cell_offsets(cond_order)
+            Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
+                np.asarray(contrast, dtype=float))
+            K = Ucoef.shape[1]
+            Gz = _behaviour_state(eng, cells)["Gz"]
+            Q, _, _ = eng.rb_coef(Y, idx_dev, cells, Ucoef, scatter=False)
+            d2, _ = eng.nspace_coef(Gz, Q)
+            Lop = None
+        else:
+            Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
+            K = E.shape[1]
+            d2, _ = eng.nspace(E, idx_dev)
+        counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg in ("mct", "rb") else 0.0)
         dist.allreduce_sum_(counts)
         s_hat = dist.gather_rows(s_hat, niter, lo)
         counts, s_list = eng.to_host(counts, s_hat)
@@ -197,6 +229,8 @@ class _ResampleTestPLS(ResampleTest):
         debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
 
         def _sum_sq_crossblock():                              # sum(permuted**2) (:399): trace(Lop S G S^T Lop^T)
+            if Lop is None:
+                raise exceptions.NotImplementedError("perm_debug_dict['sum_s'] is not provided for behaviour PLS")
             if dist.world()[1] > 1:
                 raise RuntimeError("perm_debug_dict['sum_s'] is only available in single-process runs")
             d2f, _ = eng.nspace(np.ascontiguousarray(Lop.T), _index_shard(eng, indices, niter, 0, niter))
@@ -212,7 +246,12 @@ class _ResampleTestPLS(ResampleTest):
         """bootstrap_permutation.py:466-766 for the task methods (mct, cst)."""
         eng = engine if engine is not None else Engine(X)
         if indices is None:
-            indices = resample.bootstrap_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)[0]
+            indices = resample.bootstrap_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)
+        if isinstance(indices, tuple):
+            indices = indices[0]
+        if pls_alg in ("rb", "csb"):
+            return _ResampleTestPLS._bootstrap_behaviour(eng, Y, U, s, V, cond_order, niter, pls_alg, contrast,
+                                                         lvcorrs_orig, CI, indices)
         Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
         Abar = class_functions._cell_mean_operator(cond_order)
         # numerator of the bootstrap ratios = the original salience (:700-703); also the pivot that keeps
@@ -257,6 +296,39 @@ class _ResampleTestPLS(ResampleTest):
             return eng.salience(E, _index_shard(eng, indices, niter, 0, niter)).cpu().numpy()
         debug.set_lazy("right_sv_sampled", _right)
         return conf_int, std_errs_h, boot_ratios_h, debug
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _bootstrap_behaviour(eng, Y, U, s, V, cond_order, niter, pls_alg, contrast, lvcorrs_orig, CI, indices):
+        """bootstrap_permutation.py:537-675, 695-766 for rb / csb: X and Y rows are resampled together, the
+        block z-scores of X change with every draw, so X is streamed once per bootstrap batch (K5)."""
+        cells = _cell_offsets(cond_order)
+        Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
+            np.asarray(contrast, dtype=float))
+        nb = Y.shape[1]
+        Vd = eng.to_device(V, torch.float64)
+        numer = Vd * eng.to_device(np.asarray(s, dtype=float), torch.float64) if contrast is None else Vd
+        Xc = _behaviour_state(eng, cells)["Xc"]
+        lo, hi = dist.shard(niter)
+        idx_dev = _index_shard(eng, indices, niter, lo, hi)
+        if hi > lo:
+            Q, W, Yz = eng.rb_coef(Y, idx_dev, cells, Ucoef, scatter=True, want_yz=True)
+            s1, s2, T, nrm2 = eng.rb_boot(Xc, Q, W, cells, pivot=numer)
+            LV = eng.rb_lvcorr(T, nrm2, Yz, idx_dev, cells, nb)                 # (:636-642, 668-675)
+        else:
+            s1 = torch.zeros_like(numer); s2 = torch.zeros_like(numer)
+            LV = torch.zeros((0, (len(cells) - 1) * nb, Ucoef.shape[1]), dtype=torch.float64, device=eng.device)
+        dist.allreduce_packed_([s1, s2])
+        std_errs, boot_ratios = eng.boot_finalize(s1, s2, niter, numer=numer)    # (:695-703)
+        LV = dist.gather_rows(LV, niter, lo)
+        std_L, std_errs_h, boot_ratios_h, LV_h = eng.to_host(eng.colstd(LV), std_errs, boot_ratios, LV)
+        z = norm.ppf(1 - (1 - CI) / 2)
+        half = std_L * z                                                        # (:723-725)
+        conf_int = (lvcorrs_orig - half, lvcorrs_orig + half)
+        debug = _LazyDebugDict()
+        debug["left_sv_sampled"] = LV_h
+        debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
+        return conf_int, std_errs_h, boot_ratios_h, LV_h, debug
 
     # ------------------------------------------------------------------------------------------
     def __repr__(self):

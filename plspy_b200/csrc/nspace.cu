@@ -14,7 +14,8 @@ namespace plsb {
 // One CTA per resample.  Thread j owns row j of H for KT columns at a time.
 template <int KT>
 __global__ void __launch_bounds__(512) nspace_kernel(const double* __restrict__ G, int N, const double* __restrict__ E,
-                                                      int K, int ldk, int koff, const int32_t* __restrict__ idx,
+                                                      long long e_stride, int K, int ldk, int koff,
+                                                      const int32_t* __restrict__ idx,
                                                       const double* __restrict__ Lmat, int Kt,
                                                       double* __restrict__ d2, double* __restrict__ T) {
     extern __shared__ __align__(16) double sm[];
@@ -23,9 +24,10 @@ __global__ void __launch_bounds__(512) nspace_kernel(const double* __restrict__ 
     double* dn = Hs + (size_t)N * K;      // [K] squared norms, then 1/sqrt
     int* ids = reinterpret_cast<int*>(dn + K);   // [N]
     const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int32_t* my = idx + (size_t)r * N;
-    for (int i = tid; i < N * K; i += nt) Es[i] = E[(size_t)(i / K) * ldk + koff + i % K];
-    for (int i = tid; i < N; i += nt) ids[i] = my[i];
+    // e_stride != 0: explicit per-resample coefficient matrices (behaviour PLS); idx == NULL: identity
+    const double* Er = E + (size_t)r * e_stride;
+    for (int i = tid; i < N * K; i += nt) Es[i] = Er[(size_t)(i / K) * ldk + koff + i % K];
+    for (int i = tid; i < N; i += nt) ids[i] = idx ? idx[(size_t)r * N + i] : i;
     __syncthreads();
 
     for (int j = tid; j < N; j += nt) {
@@ -172,14 +174,15 @@ __global__ void __launch_bounds__(256) colstd_kernel(const double* __restrict__ 
 }
 
 template <int KT>
-static int launch_nspace(const double* G, int N, const double* E, int K, int ldk, int koff, const int32_t* idx, int R,
+static int launch_nspace(const double* G, int N, const double* E, long long e_stride, int K, int ldk, int koff,
+                         const int32_t* idx, int R,
                          const double* Lmat, int Kt, double* d2, double* T, cudaStream_t st) {
     size_t smem = ((size_t)2 * N * K + K) * sizeof(double) + (size_t)N * sizeof(int);
     PLSB_CUDA(cudaFuncSetAttribute(nspace_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = (int)cdiv(N, 32) * 32;
     if (threads > 512) threads = 512;
     if (threads < 128) threads = 128;
-    nspace_kernel<KT><<<R, threads, smem, st>>>(G, N, E, K, ldk, koff, idx, Lmat, Kt, d2, T);
+    nspace_kernel<KT><<<R, threads, smem, st>>>(G, N, E, e_stride, K, ldk, koff, idx, Lmat, Kt, d2, T);
     PLSB_LAUNCH_CHECK("nspace_kernel");
     return PLSB200_OK;
 }
@@ -188,13 +191,8 @@ static int launch_nspace(const double* G, int N, const double* E, int K, int ldk
 
 using namespace plsb;
 
-extern "C" int plsb200_nspace_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
-                                  const double* Lmat, int Kt, double* d2, double* T, void* stream) {
-    PLSB_CHECK_ARG(G && E && idx && d2, "nspace_f64: null pointer");
-    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "nspace_f64: bad shape N=%d K=%d R=%d", N, K, R);
-    PLSB_CHECK_ARG((T == nullptr) || (Lmat != nullptr && Kt > 0), "nspace_f64: T requested without Lmat");
-    if (R == 0) return PLSB200_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+static int nspace_dispatch(const double* G, int N, const double* E, long long e_stride, int K, const int32_t* idx,
+                           int R, const double* Lmat, int Kt, double* d2, double* T, cudaStream_t st) {
     // columns are independent: chunk K so that E and H chunks (2 * N * Kc doubles) fit in shared memory
     const size_t budget = 200 * 1024;
     int kc = K;
@@ -206,14 +204,32 @@ extern "C" int plsb200_nspace_f64(const double* G, int N, const double* E, int K
     for (int k0 = 0; k0 < K; k0 += kc) {
         const int kw = K - k0 < kc ? K - k0 : kc;
         int rc;
-        if (kw <= 4) rc = launch_nspace<4>(G, N, E, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 8) rc = launch_nspace<8>(G, N, E, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 12) rc = launch_nspace<12>(G, N, E, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 16) rc = launch_nspace<16>(G, N, E, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else rc = launch_nspace<24>(G, N, E, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        if (kw <= 4) rc = launch_nspace<4>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        else if (kw <= 8) rc = launch_nspace<8>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        else if (kw <= 12) rc = launch_nspace<12>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        else if (kw <= 16) rc = launch_nspace<16>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        else rc = launch_nspace<24>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
         if (rc != PLSB200_OK) return rc;
     }
     return PLSB200_OK;
+}
+
+extern "C" int plsb200_nspace_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
+                                  const double* Lmat, int Kt, double* d2, double* T, void* stream) {
+    PLSB_CHECK_ARG(G && E && idx && d2, "nspace_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "nspace_f64: bad shape N=%d K=%d R=%d", N, K, R);
+    PLSB_CHECK_ARG((T == nullptr) || (Lmat != nullptr && Kt > 0), "nspace_f64: T requested without Lmat");
+    if (R == 0) return PLSB200_OK;
+    return nspace_dispatch(G, N, E, 0, K, idx, R, Lmat, Kt, d2, T, (cudaStream_t)stream);
+}
+
+extern "C" int plsb200_nspace_coef_f64(const double* G, int N, const double* C, int K, int R, const double* Lmat,
+                                       int Kt, double* d2, double* T, void* stream) {
+    PLSB_CHECK_ARG(G && C && d2, "nspace_coef_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "nspace_coef_f64: bad shape N=%d K=%d R=%d", N, K, R);
+    PLSB_CHECK_ARG((T == nullptr) || (Lmat != nullptr && Kt > 0), "nspace_coef_f64: T requested without Lmat");
+    if (R == 0) return PLSB200_OK;
+    return nspace_dispatch(G, N, C, (long long)N * K, K, nullptr, R, Lmat, Kt, d2, T, (cudaStream_t)stream);
 }
 
 extern "C" int plsb200_perm_count_f64(const double* d2, int R, int K, const double* s_ref, const double* totcov_ref,

@@ -97,17 +97,21 @@ class Engine:
         return [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev) - 1, 2)]
 
     # ------------------------------------------------------------------ kernels
+    def gram_of(self, M):
+        """K1: M M^T for a device matrix M (rows x p)."""
+        n, p, ld = int(M.shape[0]), int(M.shape[1]), int(M.stride(0))
+        with torch.cuda.device(self.device):
+            ws = self._ws(lib.plsb200_gram_f64_workspace(n, p))
+            G = self._empty(n, n)
+            check(lib.plsb200_gram_f64(self._p(M), n, p, ld, self._p(G), self._p(ws), ws.numel(), self._stream()),
+                  "gram_f64")
+        return G
+
     @property
     def G(self):
-        """K1: G = X X^T (N x N)."""
+        """G = X X^T (N x N), computed once per engine."""
         if self._G is None:
-            with torch.cuda.device(self.device):
-                need = lib.plsb200_gram_f64_workspace(self.N, self.p)
-                ws = self._ws(need)
-                G = self._empty(self.N, self.N)
-                check(lib.plsb200_gram_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(G), self._p(ws),
-                                           ws.numel(), self._stream()), "gram_f64")
-            self._G = G
+            self._G = self.gram_of(self.X)
         return self._G
 
     def xv(self, V):
@@ -120,6 +124,18 @@ class Engine:
             check(lib.plsb200_xv_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(V), K, self._p(out),
                                      self._p(ws), ws.numel(), self._stream()), "xv_f64")
         return out
+
+    def nspace_coef(self, G, C, Lmat=None):
+        """d2[r,k] = C_r[:,k]^T G C_r[:,k] for explicit per-resample coefficients C (R x N x K)."""
+        R, N, K = int(C.shape[0]), int(C.shape[1]), int(C.shape[2])
+        d2 = self._empty(R, K)
+        T = None; Kt = 0
+        if Lmat is not None:
+            Lmat = self.to_device(Lmat, F64); Kt = int(Lmat.shape[0]); T = self._empty(R, Kt, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_nspace_coef_f64(self._p(G), N, self._p(C), K, R, self._p(Lmat), Kt, self._p(d2),
+                                              self._p(T), self._stream()), "nspace_coef_f64")
+        return d2, T
 
     def nspace(self, E, idx, Lmat=None):
         """d2[r,k] = ||X^T C_r[:,k]||^2 and (optionally) T[r] = Lmat G C_r diag(1/sqrt(d2))."""
@@ -255,3 +271,66 @@ class Engine:
             check(lib.plsb200_split_svd_f64(self._p(S11), self._p(S12), self._p(S22), K, S, self._p(s1), self._p(st),
                                             self._p(ur), self._p(vr), self._p(s2), self._stream()), "split_svd_f64")
         return s1, st, ur, vr, s2
+
+    # ------------------------------------------------------------------ behaviour PLS (K5)
+    def cell_standardize(self, cell_start, want_z=True):
+        """Xc = X - block means, Z = block z-score(X) / sqrt(n) (both N x p, dense)."""
+        cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
+        Xc = self._empty(self.N, self.p)
+        Z = self._empty(self.N, self.p) if want_z else None
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_cell_standardize_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(cs),
+                                                   int(cs.numel()) - 1, self._p(Xc), self._p(Z), self._stream()),
+                  "cell_standardize_f64")
+        return Xc, Z
+
+    def rb_coef(self, Y, idx, cell_start, U, scatter, want_yz=False):
+        Y = self.to_device(Y, F64); U = self.to_device(U, F64)
+        cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
+        idx = self.to_device(idx, I32) if idx is not None else None
+        N, nb = int(Y.shape[0]), int(Y.shape[1])
+        R = int(idx.shape[0]) if idx is not None else 1
+        Kc = int(U.shape[1])
+        Q = self._empty(R, N, Kc)
+        W = self._empty(R, N) if scatter else None
+        Yz = self._empty(R, N, nb) if want_yz else None
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_rb_coef_f64(self._p(Y), N, nb, self._p(idx), R, self._p(cs), int(cs.numel()) - 1,
+                                          self._p(U), Kc, int(bool(scatter)), self._p(Q), self._p(W), self._p(Yz),
+                                          self._stream()), "rb_coef_f64")
+        return Q, W, Yz
+
+    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, max_ws_bytes=512 << 20):
+        """p-space pass over all bootstraps in Q: returns (sum, sumsq) of VS - pivot (p x K),
+        T (R x N x K) = Xc @ VS_b and nrm2 (R x K)."""
+        cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
+        R, N, K = int(Q.shape[0]), int(Q.shape[1]), int(Q.shape[2])
+        p = int(Xc.shape[1])
+        s1 = torch.zeros(p, K, dtype=F64, device=self.device); s2 = torch.zeros_like(s1)
+        T = self._empty(R, N, K); nrm2 = self._empty(R, K)
+        if pivot is not None:
+            pivot = self.to_device(pivot, F64)
+        per = lib.plsb200_rb_boot_f64_workspace(N, p, K, 1)
+        nbt = max(1, min(R, int(max_ws_bytes // max(per, 1))))
+        with torch.cuda.device(self.device):
+            ws = self._ws(per * nbt)
+            self._mark("rb_boot")
+            for b0 in range(0, R, nbt):
+                n = min(nbt, R - b0)
+                check(lib.plsb200_rb_boot_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n, self._p(cs),
+                                              int(cs.numel()) - 1, self._p(pivot), self._p(s1), self._p(s2),
+                                              self._p(T), self._p(nrm2), self._p(ws), ws.numel(), self._stream()),
+                      "rb_boot_f64")
+            self._mark("rb_boot")
+        return s1, s2, T, nrm2
+
+    def rb_lvcorr(self, T, nrm2, Yz, idx, cell_start, nb):
+        cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
+        idx = self.to_device(idx, I32) if idx is not None else None
+        R, N, K = int(T.shape[0]), int(T.shape[1]), int(T.shape[2])
+        ncell = int(cs.numel()) - 1
+        LV = self._empty(R, ncell * nb, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_rb_lvcorr_f64(self._p(T), self._p(nrm2), self._p(Yz), self._p(idx), N, nb, K, R,
+                                            self._p(cs), ncell, self._p(LV), self._stream()), "rb_lvcorr_f64")
+        return LV

@@ -118,7 +118,7 @@ def test_na_placeholders_and_no_gpu_work_when_skipped():
 
 def test_unimplemented_methods_fail_loudly():
     import plspy_b200
-    g = _load("rb_bal")
+    g = _load("mb_full")
     with pytest.raises(plspy_b200.exceptions.NotImplementedError):
         _run_product(g)
 
@@ -155,3 +155,47 @@ def test_split_half_matches_reference_golden(name):
     for k in g:
         if k.startswith("sh_pls_") and "dist" not in k:
             np.testing.assert_allclose(np.asarray(sh[k[3:]]), g[k], rtol=1e-7, atol=1e-9, err_msg=k)
+
+
+BEH_CASES = [c for c in golden_cases() if c.startswith(("rb", "csb"))]
+
+
+@pytest.mark.parametrize("name", BEH_CASES)
+def test_behaviour_methods_match_reference_golden(name):
+    g = _load(name)
+    res = _run_product(g)
+    rt = res.resample_tests
+    live = np.abs(g["s"]) > 1e-8
+    if int(g["nperm"]):
+        np.testing.assert_array_equal(rt.perm_debug_dict["indices"], g["perm_idx_beh"])
+        np.testing.assert_array_equal(rt.permute_ratio, g["permute_ratio"])
+        np.testing.assert_array_equal(rt.stepdown_ratio, g["stepdown_ratio"])
+        if g["perm_s_last"].size:
+            np.testing.assert_allclose(rt.perm_debug_dict["s_list"][-1][live], g["perm_s_last"][live], rtol=1e-9)
+    if int(g["nboot"]):
+        np.testing.assert_array_equal(rt.boot_debug_dict["indices"], g["boot_idx"])
+        np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-8)
+        np.testing.assert_allclose(rt.boot_ratios[:, live], g["boot_ratios"][:, live], rtol=1e-8)
+        np.testing.assert_allclose(rt.LVcorr[:, :, live], g["LVcorr"][:, :, live], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(rt.conf_ints[1][:, live], g["conf_hi"][:, live], rtol=1e-8, atol=1e-9)
+
+
+def test_rb_matches_oracle_cfg2_shape():
+    """BASELINE cfg 2 shape (rb, 2 groups x 20 subj x 3 cond x 50k voxels, 4 behaviours), 40 perm / 40 boot."""
+    import plspy_b200
+    rs = np.random.RandomState(77)
+    groups, C, p, nb = (20, 20), 3, 50000, 4
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)) + 10.0
+    Y = rs.standard_normal((N, nb)) + 0.3 * X[:, :nb]
+    np.random.seed(9)
+    o = oracle.run_full("rb", X.copy(), groups, C, Y=Y.copy(), nperm=40, nboot=40)
+    res = plspy_b200.PLS(X.copy(), groups, C, Y=Y.copy(), num_perm=40, num_boot=40, pls_method="rb",
+                         perm_indices=o["perm_idx_beh"], boot_indices=o["boot_idx"])
+    rt = res.resample_tests
+    np.testing.assert_array_equal(rt.permute_ratio, o["perm"]["permute_ratio"])
+    np.testing.assert_allclose(rt.perm_debug_dict["s_list"], o["perm"]["s_hat"], rtol=1e-9)
+    np.testing.assert_allclose(rt.std_errs, o["boot"]["std_errs"], rtol=1e-8)
+    np.testing.assert_allclose(rt.boot_ratios, o["boot"]["boot_ratios"], rtol=1e-8)
+    np.testing.assert_allclose(rt.LVcorr, o["boot"]["LVcorr"], rtol=1e-7, atol=1e-9)
