@@ -88,9 +88,11 @@ int plsb200_perm_count_f64(const double* d2, int R, int K, const double* s_ref, 
                            double thresh, const double* mb_total, int64_t* counts, double* s_hat,
                            void* stream);
 
-/* ---- U_hat_r = Lop (Ku x N) . XL[idx_r, :] (N x K)  -> Uhat: R x Ku x K   (bootstrap_permutation.py:617) */
-int plsb200_uhat_f64(const double* XL, int N, int K, const double* Lop, int Ku, const int32_t* idx, int R,
-                     double* Uhat, void* stream);
+/* ---- U_hat_r = Lop (Ku x N) . XL_r[idx_r, :] (N x K)  -> Uhat: R x Ku x K   (bootstrap_permutation.py:617).
+ * xl_stride = 0: one latent matrix XL shared by all resamples; otherwise XL_r = XL + r*xl_stride
+ * (multiblock Tdistrib, :654-656, :665-666).  idx may be NULL (identity).                            */
+int plsb200_uhat_f64(const double* XL, int64_t xl_stride, int N, int K, const double* Lop, int Ku,
+                     const int32_t* idx, int R, double* Uhat, void* stream);
 
 /* ---- K4: bootstrap salience moments ---------------------------------------------------------------
  * The batched GEMM  VS[v, (r,k)] = sum_i X[i, v] . C_r[i, k]  over all R resamples, with
@@ -150,9 +152,17 @@ int plsb200_rb_coef_f64(const double* Y, int N, int nb, const int32_t* idx, int 
                         void* stream);
 size_t plsb200_rb_boot_f64_workspace(int N, int64_t p, int K, int nbt);
 int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
-                        int nbt, const int32_t* cell_start, int ncell, const double* pivot, double* sum,
-                        double* sumsq, double* T, double* nrm2, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        int nbt, const int32_t* cell_start, int ncell, int unit_cells, const double* pivot,
+                        double* sum, double* sumsq, double* T, double* nrm2, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* multiblock glue (class_functions.py:454-516): the last `unit_cells` blocks of rb_boot are plain linear rows
+ * (task part of the multiblock matrix, no standardisation).
+ * scatter_coef: C[r] (N x K) = scatter(E, idx_r) written out explicitly.
+ * coef_project: C2[r] (N x K) = C1[r] (N x M) . diag(1/sqrt(d2[r])) . Uc (M x K): row-normalise the M multiblock
+ *   rows (d2 = their squared norms) and project on the design weights.                                */
+int plsb200_scatter_coef_f64(const double* E, int N, int K, const int32_t* idx, int R, double* C, void* stream);
+int plsb200_coef_project_f64(const double* C1, int N, int M, const double* d2, const double* Uc, int K, int R,
+                             double* C2, void* stream);
 int plsb200_rb_lvcorr_f64(const double* T, const double* nrm2, const double* Yz, const int32_t* idx, int N, int nb,
                           int K, int R, const int32_t* cell_start, int ncell, double* LVcorr, void* stream);
 

@@ -45,8 +45,11 @@ SIGNATURES = {
                                    c_double_p, c_double_p, c_void_p]),
     "plsb200_perm_count_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_double, c_double_p,
                                        c_void_p, c_double_p, c_void_p]),
-    "plsb200_uhat_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p,
+    "plsb200_uhat_f64": (c_int, [c_double_p, c_int64, c_int, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p,
                                  c_void_p]),
+    "plsb200_scatter_coef_f64": (c_int, [c_double_p, c_int, c_int, c_int32_p, c_int, c_double_p, c_void_p]),
+    "plsb200_coef_project_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_int, c_int, c_double_p,
+                                         c_void_p]),
     "plsb200_boot_coef_bytes": (c_size_t, [c_int, c_int, c_int]),
     "plsb200_boot_coef_pack_f64": (c_int, [c_double_p, c_int, c_int, c_int32_p, c_int, c_double_p, c_void_p]),
     "plsb200_boot_moments_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),
@@ -68,8 +71,8 @@ SIGNATURES = {
                                     c_int, c_double_p, c_double_p, c_double_p, c_void_p]),
     "plsb200_rb_boot_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "plsb200_rb_boot_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_double_p, c_int, c_int, c_int,
-                                    c_int32_p, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
-                                    c_void_p, c_size_t, c_void_p]),
+                                    c_int32_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                    c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_rb_lvcorr_f64": (c_int, [c_double_p, c_double_p, c_double_p, c_int32_p, c_int, c_int, c_int, c_int,
                                       c_int32_p, c_int, c_double_p, c_void_p]),
     "plsb200_salience_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,

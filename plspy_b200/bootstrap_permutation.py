@@ -126,6 +126,165 @@ def _behaviour_state(eng, cells):
     return st
 
 
+def _multiblock_state(eng, cond_order, bscan):
+    """Per-engine cache for mb/cmb: the bscan rows of X block-centred (Xcb) and z-scored (Zb), the stacked
+    matrices W1 = [X; Zb] (permutations, with its Gram matrix) and W2 = [Xcb; X] (bootstraps), and the
+    column maps of the multiblock row order (per group: C task rows, then |bscan|*nb behaviour rows,
+    class_functions.py:496-514)."""
+    co = np.asarray(cond_order)
+    key = ("mb", tuple(co.reshape(-1).tolist()), tuple(bscan))
+    st = getattr(eng, "_multiblock", None)
+    if st is not None and st["key"] == key:
+        return st
+    rows_b = np.concatenate([np.full(co[g, c], c in list(bscan), dtype=bool)
+                             for g in range(co.shape[0]) for c in range(co.shape[1])]).nonzero()[0]
+    cells_b = _cell_offsets(co[:, bscan])
+    Xb = eng.X.index_select(0, torch.as_tensor(rows_b, device=eng.device))
+    Xcb, Zb = eng.cell_standardize(cells_b, M=Xb)
+    W1 = torch.cat([eng.X, Zb], dim=0)
+    st = {"key": key, "rows_b": rows_b, "cells_b": cells_b, "Xcb": Xcb, "Nb": int(Xb.shape[0]),
+          "Gw": eng.gram_of(W1), "W2": torch.cat([Xcb, eng.X], dim=0)}
+    del W1, Zb, Xb
+    eng._multiblock = st
+    return st
+
+
+def _multiblock_columns(cond_order, bscan, nb):
+    co = np.asarray(cond_order)
+    G, C = co.shape
+    nbs = len(bscan)
+    Kg = C + nbs * nb
+    task = np.array([g * Kg + c for g in range(G) for c in range(C)])
+    beh = np.array([g * Kg + C + cb * nb + j for g in range(G) for cb in range(nbs) for j in range(nb)])
+    return task, beh, G * Kg
+
+
+def _multiblock_indices(pls_alg, indices, niter, cond_order, bscan, Ybscan, boot):
+    if indices is None:
+        gen = resample.bootstrap_indices if boot else resample.permutation_indices
+        indices = gen(pls_alg, niter, cond_order, bscan=bscan, Ybscan=Ybscan)
+    if not isinstance(indices, tuple) or len(indices) != 2:
+        raise ValueError("multiblock resampling needs a (task, behaviour) pair of index matrices")
+    return indices
+
+
+def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan, Ybscan, indices):
+    """bootstrap_permutation.py:305-312, 342-347, 391-393, 413-433 for mb / cmb.  Task rows come from the
+    task-permuted X, behaviour rows from the ORIGINAL bscan rows of X with globally permuted Ybscan; every
+    row is L2-normalised.  With W = [X; Zb] all of it is N-space: row norms and projected norms are
+    quadratic forms in Gw = W W^T."""
+    st = _multiblock_state(eng, cond_order, bscan)
+    nb = Ybscan.shape[1]
+    tcol, bcol, K = _multiblock_columns(cond_order, bscan, nb)
+    idx_t, idx_b = _multiblock_indices(pls_alg, indices, niter, cond_order, bscan, Ybscan, boot=False)
+    # rescaled observed singular values (:305-312); the un-normalised multiblock of the original data is a
+    # one-off host computation
+    raw = class_functions._create_multiblock(np.asarray(X) if not torch.is_tensor(X) else X.cpu().numpy(),
+                                             cond_order, pls_alg, bscan, mctype, norm_opt=False,
+                                             Xbscan=Xbscan, Ybscan=Ybscan)
+    org_s = np.sqrt(s ** 2 / np.sum(s ** 2) * np.sum(raw ** 2))
+    totcov_org = _stepdown_tail(org_s)
+    Lop = (class_functions._cell_mean_operator(cond_order) if pls_alg == "cmb"
+           else class_functions._centring_operator(cond_order, mctype))
+    Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
+        np.asarray(contrast, dtype=float))
+    Kc = Ucoef.shape[1]
+    N, Nb = eng.N, st["Nb"]
+    lo, hi = dist.shard(niter)
+    it = _index_shard(eng, idx_t, niter, lo, hi); ib = _index_shard(eng, idx_b, niter, lo, hi)
+    R = hi - lo
+    Ct = eng.scatter_coef(np.ascontiguousarray(Lop.T), it)                          # R x N x GC
+    Qb, _, _ = eng.rb_coef(Ybscan, ib, st["cells_b"], np.eye(len(bcol)), scatter=False)   # R x Nb x Kb
+    C1 = torch.zeros(R, N + Nb, K, dtype=torch.float64, device=eng.device)
+    C1[:, :N, torch.as_tensor(tcol, device=eng.device)] = Ct
+    C1[:, N:, torch.as_tensor(bcol, device=eng.device)] = Qb
+    d2row, _ = eng.nspace_coef(st["Gw"], C1)                                        # squared row norms
+    total = d2row.sum(dim=1)                                                        # ||un-normalised multiblock||_F^2
+    C2 = eng.coef_project(C1, d2row, Ucoef)
+    d2, _ = eng.nspace_coef(st["Gw"], C2)
+    if pls_alg == "mb":     # s_hat^4 rescale, compared with org_s (:419-427)
+        counts, s_hat = eng.perm_count(d2, org_s, totcov_org, 0.0, mb_total=total)
+    else:                   # cmb: raw s for the counts, rescaled org_s for the stepdown baseline (:433, :316-319)
+        counts, s_hat = eng.perm_count(d2, s, totcov_org, 0.0)
+    dist.allreduce_sum_(counts)
+    s_hat = dist.gather_rows(s_hat, niter, lo)
+    counts, s_list = eng.to_host(counts, s_hat)
+    counts = counts.astype(float)
+    debug = _LazyDebugDict()
+    debug["s_list"] = s_list
+    debug["sum_perm"] = np.sum(s_list ** 2, axis=1)
+    debug["org_s"] = org_s
+    debug.set_lazy("indices", lambda: _indices_to_host(idx_t, niter))
+    debug.set_lazy("indices_behaviour", lambda: _indices_to_host(idx_b, niter))
+    return counts[:Kc] / (niter + 1), counts[Kc:] / (niter + 1), debug
+
+
+def _boot_multiblock(eng, U, s, V, cond_order, mctype, niter, pls_alg, contrast, bscan, Ybscan, lvcorrs_orig,
+                     Tvsc_orig, CI, indices):
+    """bootstrap_permutation.py:545-554, 609-675, 695-766 for mb / cmb: independent bootstrap draws for the
+    task block (rows of X) and the behaviour block (bscan rows).  Two p-space passes per bootstrap batch:
+    (1) squared norms of the behaviour rows (their per-voxel std depends on the draw), (2) the projected
+    cross-block matrix VS = permuted^T U of the row-normalised multiblock, with fused moments and the
+    latent products [Xcb; X] @ VS needed for LVcorr and Tdistrib."""
+    st = _multiblock_state(eng, cond_order, bscan)
+    nb = Ybscan.shape[1]
+    tcol, bcol, K = _multiblock_columns(cond_order, bscan, nb)
+    idx_t, idx_b = _multiblock_indices(pls_alg, indices, niter, cond_order, bscan, Ybscan, boot=True)
+    Lop = (class_functions._cell_mean_operator(cond_order) if pls_alg == "cmb"
+           else class_functions._centring_operator(cond_order, mctype))
+    Abar = class_functions._cell_mean_operator(cond_order)
+    Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
+        np.asarray(contrast, dtype=float))
+    Kc = Ucoef.shape[1]
+    N, Nb = eng.N, st["Nb"]
+    dev = eng.device
+    Vd = eng.to_device(V, torch.float64)
+    numer = Vd * eng.to_device(np.asarray(s, dtype=float), torch.float64) if contrast is None else Vd
+    lo, hi = dist.shard(niter)
+    it = _index_shard(eng, idx_t, niter, lo, hi); ib = _index_shard(eng, idx_b, niter, lo, hi)
+    R = hi - lo
+    tcol_d = torch.as_tensor(tcol, device=dev); bcol_d = torch.as_tensor(bcol, device=dev)
+    # task rows: coefficients over the rows of X and their squared norms through G
+    Ct = eng.scatter_coef(np.ascontiguousarray(Lop.T), it)                          # R x N x GC
+    d2t, _ = eng.nspace_coef(eng.G, Ct)
+    # behaviour rows: raw (un-normalised) correlation rows and pass 1 for their squared norms
+    Qraw, Wb, Yz = eng.rb_coef(Ybscan, ib, st["cells_b"], np.eye(len(bcol)), scatter=True, want_yz=True)
+    _, _, _, nrm_b = eng.rb_boot(st["Xcb"], Qraw, Wb, st["cells_b"])
+    d2row = torch.zeros(R, K, dtype=torch.float64, device=dev)
+    d2row[:, tcol_d] = d2t
+    d2row[:, bcol_d] = nrm_b
+    C1 = torch.zeros(R, Nb + N, K, dtype=torch.float64, device=dev)                 # rows ordered like W2 = [Xcb; X]
+    C1[:, :Nb, bcol_d] = Qraw
+    C1[:, Nb:, tcol_d] = Ct
+    C2 = eng.coef_project(C1, d2row, Ucoef)                                         # R x (Nb+N) x Kc
+    Wfull = torch.cat([Wb, torch.zeros(R, N, dtype=torch.float64, device=dev)], dim=1)
+    cells2 = np.concatenate([st["cells_b"], [Nb + N]]).astype(np.int32)
+    s1, s2, T, nrm2 = eng.rb_boot(st["W2"], C2, Wfull, cells2, pivot=numer, unit_cells=1)   # pass 2
+    dist.allreduce_packed_([s1, s2])
+    std_errs, boot_ratios = eng.boot_finalize(s1, s2, niter, numer=numer)
+    LV = eng.rb_lvcorr(T[:, :Nb, :].contiguous(), nrm2, Yz, ib, st["cells_b"], nb)  # (:650, :674)
+    XV = T[:, Nb:, :].contiguous()                                                  # X @ VS_b per bootstrap
+    if pls_alg == "mb":      # cellmeans(smeanmat(X_new_T) @ V_hat) (:654-656)
+        Lop2 = Abar @ class_functions._smeanmat_operator(cond_order, mctype)
+        Td = eng.uhat(XV, Lop2, it)
+    else:                    # cmb: cellmeans(X @ norm_crossblock) (:665-666)
+        Td = eng.uhat(XV, Abar, None)
+    inv = torch.where(nrm2 > 0, 1.0 / torch.sqrt(nrm2), torch.zeros_like(nrm2))
+    Td = Td * inv[:, None, :]
+    LV = dist.gather_rows(LV, niter, lo); Td = dist.gather_rows(Td, niter, lo)
+    std_L, std_T, std_errs_h, boot_ratios_h, LV_h, Td_h = eng.to_host(
+        eng.colstd(LV), eng.colstd(Td), std_errs, boot_ratios, LV, Td)
+    z = norm.ppf(1 - (1 - CI) / 2)
+    conf_int = (lvcorrs_orig - std_L * z, lvcorrs_orig + std_L * z)                 # (:723-725)
+    conf_int_T = (Tvsc_orig - std_T * z, Tvsc_orig + std_T * z)                     # (:732-734)
+    debug = _LazyDebugDict()
+    debug["left_sv_sampled"] = LV_h
+    debug["Tdistrib"] = Td_h
+    debug.set_lazy("indices", lambda: _indices_to_host(idx_t, niter))
+    debug.set_lazy("indices_behaviour", lambda: _indices_to_host(idx_b, niter))
+    return conf_int, conf_int_T, std_errs_h, boot_ratios_h, LV_h, debug
+
+
 def _task_operators(pls_alg, cond_order, mctype, U, contrast):
     """Row-space pull-back of the design-side weights: E = Lop^T @ Ucoef (N x K).
     mct: Lop = centring operator, Ucoef = U (bootstrap_permutation.py:385-387, 404);
@@ -153,10 +312,6 @@ class _ResampleTestPLS(ResampleTest):
                  CI=0.95, *, perm_indices=None, boot_indices=None, engine=None):
         self.CI = CI
         _log(f"PLS ALG: {self.pls_alg}")
-        if self.pls_alg in ("mb", "cmb") and (nperm > 0 or nboot > 0):
-            raise exceptions.NotImplementedError(
-                f"{self._pls_types.get(self.pls_alg, self.pls_alg)}: permutation/bootstrap tests are not yet "
-                "available on the B200 path (no CPU fallback is provided).")
         eng = engine if engine is not None else (Engine(X) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
         if nperm > 0:
@@ -190,6 +345,9 @@ class _ResampleTestPLS(ResampleTest):
         """bootstrap_permutation.py:265-464.  `s` is thresholded in place like the reference (:295)."""
         eng = engine if engine is not None else Engine(X)
         s[np.abs(s) < threshold] = 0
+        if pls_alg in ("mb", "cmb"):
+            return _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan,
+                                    Ybscan, indices)
         org_s = np.copy(s)
         totcov_org = _stepdown_tail(org_s)
         behaviour = pls_alg in ("rb", "csb")
@@ -247,6 +405,9 @@ class _ResampleTestPLS(ResampleTest):
         eng = engine if engine is not None else Engine(X)
         if indices is None:
             indices = resample.bootstrap_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)
+        if pls_alg in ("mb", "cmb"):
+            return _boot_multiblock(eng, U, s, V, cond_order, mctype, niter, pls_alg, contrast, bscan, Ybscan,
+                                    lvcorrs_orig, Tvsc_orig, CI, indices)
         if isinstance(indices, tuple):
             indices = indices[0]
         if pls_alg in ("rb", "csb"):

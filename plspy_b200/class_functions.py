@@ -209,3 +209,26 @@ def _get_Busc(Bu, n_cond, Ybscan, cond_order, bscan):
             out.append(Ybscan[row:row + n] @ Bu[lv])
             row += n
     return np.vstack(out)
+
+
+def _smeanmat_operator(cond_order, mctype):
+    """B (N x N) with resample._calculate_smeanmat(X) = B @ X: subject-level centring used for the
+    multiblock bootstrap Tdistrib (resample.py:224-287)."""
+    co = np.asarray(cond_order)
+    G, C = co.shape
+    N = int(co.sum())
+    gsz = co.sum(axis=1)
+    I = np.eye(N)
+    grp = np.repeat(_group_mean_operator(co), gsz, axis=0)
+    cnd = np.repeat(np.tile(_grand_condition_operator(co), (G, 1)), co.reshape(-1), axis=0)
+    if mctype == 0:
+        return I - grp
+    if mctype == 1:
+        return I - cnd
+    if mctype == 2:
+        return I - np.full((N, N), 1.0 / N)
+    if mctype == 3:
+        grand = _grand_condition_operator(co).mean(axis=0, keepdims=True)
+        return I - grp - cnd + np.repeat(grand, N, axis=0)
+    from . import exceptions
+    raise exceptions.NotImplementedError("invalid mctype")

@@ -120,13 +120,17 @@ __global__ void perm_count_kernel(const double* __restrict__ d2, int R, int K, c
 }
 
 // U_hat_r = Lop (Ku x N) . XL[idx_r, :]   one CTA per resample
-__global__ void uhat_kernel(const double* __restrict__ XL, int N, int K, const double* __restrict__ Lop, int Ku,
-                            const int32_t* __restrict__ idx, double* __restrict__ Uhat) {
+__global__ void uhat_kernel(const double* __restrict__ XL, long long xl_stride, int N, int K,
+                            const double* __restrict__ Lop, int Ku, const int32_t* __restrict__ idx,
+                            double* __restrict__ Uhat) {
     extern __shared__ __align__(16) double smu[];
     double* Xs = smu;   // gathered XL rows [N][K]
     const int r = blockIdx.x;
-    const int32_t* my = idx + (size_t)r * N;
-    for (int i = threadIdx.x; i < N * K; i += blockDim.x) Xs[i] = XL[(size_t)my[i / K] * K + i % K];
+    const double* xl = XL + (size_t)r * xl_stride;       // xl_stride != 0: one latent matrix per resample
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+        const int src = idx ? idx[(size_t)r * N + i / K] : i / K;
+        Xs[i] = xl[(size_t)src * K + i % K];
+    }
     __syncthreads();
     for (int o = threadIdx.x; o < Ku * K; o += blockDim.x) {
         const int c = o / K, k = o % K;
@@ -245,9 +249,9 @@ extern "C" int plsb200_perm_count_f64(const double* d2, int R, int K, const doub
     return PLSB200_OK;
 }
 
-extern "C" int plsb200_uhat_f64(const double* XL, int N, int K, const double* Lop, int Ku, const int32_t* idx, int R,
-                                double* Uhat, void* stream) {
-    PLSB_CHECK_ARG(XL && Lop && idx && Uhat, "uhat_f64: null pointer");
+extern "C" int plsb200_uhat_f64(const double* XL, int64_t xl_stride, int N, int K, const double* Lop, int Ku,
+                                const int32_t* idx, int R, double* Uhat, void* stream) {
+    PLSB_CHECK_ARG(XL && Lop && Uhat, "uhat_f64: null pointer");
     PLSB_CHECK_ARG(N > 0 && K > 0 && Ku > 0 && R >= 0, "uhat_f64: bad shape");
     if (R == 0) return PLSB200_OK;
     size_t smem = (size_t)N * K * sizeof(double);
@@ -256,7 +260,7 @@ extern "C" int plsb200_uhat_f64(const double* XL, int N, int K, const double* Lo
         return PLSB200_EUNSUPPORTED;
     }
     PLSB_CUDA(cudaFuncSetAttribute(uhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uhat_kernel<<<R, 256, smem, (cudaStream_t)stream>>>(XL, N, K, Lop, Ku, idx, Uhat);
+    uhat_kernel<<<R, 256, smem, (cudaStream_t)stream>>>(XL, xl_stride, N, K, Lop, Ku, idx, Uhat);
     PLSB_LAUNCH_CHECK("uhat_kernel");
     return PLSB200_OK;
 }

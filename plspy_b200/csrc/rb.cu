@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(RB_VT) rb_boot_kernel(const double* __restrict
                                                        const double* __restrict__ Q, const double* __restrict__ W,
                                                        int Kq, int k0, int kc, int b0, int nbt,
                                                        const int32_t* __restrict__ cell_start, int ncell,
+                                                       int unit_cells,
                                                        const double* __restrict__ pivot, int Kfull,
                                                        double* __restrict__ sum, double* __restrict__ sumsq,
                                                        double* __restrict__ Tpart, double* __restrict__ Npart) {
@@ -171,8 +172,11 @@ __global__ void __launch_bounds__(RB_VT) rb_boot_kernel(const double* __restrict
             }
             const double var = m2 - m1 * m1;
             // a block whose resampled rows are all identical has var == 0 in exact arithmetic (nan -> 0 in
-            // the reference); guard the one-pass formula with a relative threshold
-            const double sc = (var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * (double)(e - s)) : 0.0;
+            // the reference); guard the one-pass formula with a relative threshold.  The last `unit_cells`
+            // blocks are plain linear rows (multiblock task part): no standardisation.
+            const double sc = c >= ncell - unit_cells
+                                  ? 1.0
+                                  : ((var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * (double)(e - s)) : 0.0);
 #pragma unroll
             for (int k = 0; k < KC; ++k) vs[k] = fma(sc, P[k], vs[k]);
         }
@@ -297,9 +301,75 @@ __global__ void __launch_bounds__(256) rb_lvcorr_kernel(const double* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Explicit scatter of the row-space weights: C[r][o][k] = sum_{i: idx[r][i] == o} E[i][k]  (deterministic scan)
+__global__ void __launch_bounds__(256) scatter_coef_kernel(const double* __restrict__ E, int N, int K,
+                                                          const int32_t* __restrict__ idx, double* __restrict__ C) {
+    extern __shared__ int sids[];
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sids[i] = idx[(size_t)r * N + i];
+    __syncthreads();
+    for (int o = threadIdx.x; o < N * K; o += blockDim.x) {
+        const int row = o / K, k = o % K;
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i)
+            if (sids[i] == row) acc += E[(size_t)i * K + k];
+        C[(size_t)r * N * K + o] = acc;
+    }
+}
+
+// C2[r][i][k] = sum_m C1[r][i][m] * rn[r][m] * Uc[m][k],  rn = 1/sqrt(d2) (0 where d2 <= 0):
+// normalise the multiblock rows (class_functions.py:503-505) and project on the design weights.
+__global__ void __launch_bounds__(256) coef_project_kernel(const double* __restrict__ C1, int N, int M,
+                                                          const double* __restrict__ d2, const double* __restrict__ Uc,
+                                                          int K, double* __restrict__ C2) {
+    extern __shared__ __align__(16) double smc[];
+    double* Us = smc;              // [M][K] scaled by rn
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+        const double d = d2[(size_t)r * M + i / K];
+        Us[i] = Uc[i] * (d > 0.0 ? 1.0 / sqrt(d) : 0.0);
+    }
+    __syncthreads();
+    const double* c1 = C1 + (size_t)r * N * M;
+    for (int o = threadIdx.x; o < N * K; o += blockDim.x) {
+        const int row = o / K, k = o % K;
+        double acc = 0.0;
+        for (int m = 0; m < M; ++m) acc = fma(c1[(size_t)row * M + m], Us[m * K + k], acc);
+        C2[(size_t)r * N * K + o] = acc;
+    }
+}
+
 }  // namespace plsb
 
 using namespace plsb;
+
+extern "C" int plsb200_scatter_coef_f64(const double* E, int N, int K, const int32_t* idx, int R, double* C,
+                                        void* stream) {
+    PLSB_CHECK_ARG(E && idx && C, "scatter_coef_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "scatter_coef_f64: bad shape");
+    if (R == 0) return PLSB200_OK;
+    scatter_coef_kernel<<<R, 256, (size_t)N * sizeof(int), (cudaStream_t)stream>>>(E, N, K, idx, C);
+    PLSB_LAUNCH_CHECK("scatter_coef_kernel");
+    return PLSB200_OK;
+}
+
+extern "C" int plsb200_coef_project_f64(const double* C1, int N, int M, const double* d2, const double* Uc, int K,
+                                        int R, double* C2, void* stream) {
+    PLSB_CHECK_ARG(C1 && d2 && Uc && C2, "coef_project_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && M > 0 && K > 0 && R >= 0, "coef_project_f64: bad shape");
+    if (R == 0) return PLSB200_OK;
+    size_t smem = (size_t)M * K * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_err("coef_project_f64: M*K too large for shared memory");
+        return PLSB200_EUNSUPPORTED;
+    }
+    PLSB_CUDA(cudaFuncSetAttribute(coef_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    coef_project_kernel<<<R, 256, smem, (cudaStream_t)stream>>>(C1, N, M, d2, Uc, K, C2);
+    PLSB_LAUNCH_CHECK("coef_project_kernel");
+    return PLSB200_OK;
+}
+
 
 extern "C" int plsb200_cell_standardize_f64(const double* X, int N, int64_t p, int64_t ldx, const int32_t* cell_start,
                                             int ncell, double* Xc, double* Z, void* stream) {
@@ -336,7 +406,8 @@ extern "C" size_t plsb200_rb_boot_f64_workspace(int N, int64_t p, int K, int nbt
 }
 
 extern "C" int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
-                                   int nbt, const int32_t* cell_start, int ncell, const double* pivot, double* sum,
+                                   int nbt, const int32_t* cell_start, int ncell, int unit_cells, const double* pivot,
+                                   double* sum,
                                    double* sumsq, double* T, double* nrm2, void* workspace, size_t workspace_bytes,
                                    void* stream) {
     PLSB_CHECK_ARG(Xc && Q && W && cell_start && sum && sumsq && T && nrm2 && workspace, "rb_boot_f64: null pointer");
@@ -363,7 +434,8 @@ extern "C" int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const dou
         size_t smem = ((size_t)N * KCV + N + (size_t)KCV * RB_VT + (size_t)N * (RB_VCH + 1)) * sizeof(double);      \
         if (smem > 220 * 1024) { set_err("rb_boot_f64: N=%d too large for shared memory", N); return PLSB200_EUNSUPPORTED; } \
         PLSB_CUDA(cudaFuncSetAttribute(rb_boot_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rb_boot_kernel<KCV><<<ntile, RB_VT, smem, st>>>(Xc, N, p, Q, W, K, k0, kc, b0, nbt, cell_start, ncell, pivot, K, \
+        rb_boot_kernel<KCV><<<ntile, RB_VT, smem, st>>>(Xc, N, p, Q, W, K, k0, kc, b0, nbt, cell_start, ncell,          \
+                                                        unit_cells, pivot, K,                                       \
                                                         sum, sumsq, Tpart, Npart);                                  \
     } while (0)
         if (kc <= 8) PLSB_RB_LAUNCH(8);

@@ -169,14 +169,38 @@ class Engine:
                   "perm_count_f64")
         return counts, s_hat
 
-    def uhat(self, XL, Lop, idx):
-        XL = self.to_device(XL, F64); Lop = self.to_device(Lop, F64); idx = self.to_device(idx, I32)
-        R, K, Ku = int(idx.shape[0]), int(XL.shape[1]), int(Lop.shape[0])
+    def uhat(self, XL, Lop, idx, R=None):
+        """Lop . XL[idx_r] per resample.  XL is (N x K) shared, or (R x N x K) one latent matrix per resample;
+        idx may be None (identity)."""
+        XL = self.to_device(XL, F64); Lop = self.to_device(Lop, F64)
+        idx = self.to_device(idx, I32) if idx is not None else None
+        per = XL.dim() == 3
+        if R is None:
+            R = int(idx.shape[0]) if idx is not None else int(XL.shape[0])
+        N, K, Ku = int(XL.shape[-2]), int(XL.shape[-1]), int(Lop.shape[0])
         out = self._empty(R, Ku, K)
         with torch.cuda.device(self.device):
-            check(lib.plsb200_uhat_f64(self._p(XL), self.N, K, self._p(Lop), Ku, self._p(idx), R, self._p(out),
-                                       self._stream()), "uhat_f64")
+            check(lib.plsb200_uhat_f64(self._p(XL), N * K if per else 0, N, K, self._p(Lop), Ku, self._p(idx), R,
+                                       self._p(out), self._stream()), "uhat_f64")
         return out
+
+    def scatter_coef(self, E, idx):
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, N, K = int(idx.shape[0]), int(E.shape[0]), int(E.shape[1])
+        C = self._empty(R, N, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_scatter_coef_f64(self._p(E), N, K, self._p(idx), R, self._p(C), self._stream()),
+                  "scatter_coef_f64")
+        return C
+
+    def coef_project(self, C1, d2, Uc):
+        Uc = self.to_device(Uc, F64)
+        R, N, M, K = int(C1.shape[0]), int(C1.shape[1]), int(C1.shape[2]), int(Uc.shape[1])
+        C2 = self._empty(R, N, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_coef_project_f64(self._p(C1), N, M, self._p(d2), self._p(Uc), K, R, self._p(C2),
+                                               self._stream()), "coef_project_f64")
+        return C2
 
     KMAX = 24   # columns per boot_moments launch
 
@@ -273,15 +297,16 @@ class Engine:
         return s1, st, ur, vr, s2
 
     # ------------------------------------------------------------------ behaviour PLS (K5)
-    def cell_standardize(self, cell_start, want_z=True):
-        """Xc = X - block means, Z = block z-score(X) / sqrt(n) (both N x p, dense)."""
+    def cell_standardize(self, cell_start, want_z=True, M=None):
+        """Xc = M - block means, Z = block z-score(M) / sqrt(n) (both rows x p, dense); M defaults to X."""
         cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
-        Xc = self._empty(self.N, self.p)
-        Z = self._empty(self.N, self.p) if want_z else None
+        M = self.X if M is None else M
+        n, p, ld = int(M.shape[0]), int(M.shape[1]), int(M.stride(0))
+        Xc = self._empty(n, p)
+        Z = self._empty(n, p) if want_z else None
         with torch.cuda.device(self.device):
-            check(lib.plsb200_cell_standardize_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(cs),
-                                                   int(cs.numel()) - 1, self._p(Xc), self._p(Z), self._stream()),
-                  "cell_standardize_f64")
+            check(lib.plsb200_cell_standardize_f64(self._p(M), n, p, ld, self._p(cs), int(cs.numel()) - 1,
+                                                   self._p(Xc), self._p(Z), self._stream()), "cell_standardize_f64")
         return Xc, Z
 
     def rb_coef(self, Y, idx, cell_start, U, scatter, want_yz=False):
@@ -300,7 +325,7 @@ class Engine:
                                           self._stream()), "rb_coef_f64")
         return Q, W, Yz
 
-    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, max_ws_bytes=512 << 20):
+    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, unit_cells=0, max_ws_bytes=512 << 20):
         """p-space pass over all bootstraps in Q: returns (sum, sumsq) of VS - pivot (p x K),
         T (R x N x K) = Xc @ VS_b and nrm2 (R x K)."""
         cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
@@ -318,7 +343,8 @@ class Engine:
             for b0 in range(0, R, nbt):
                 n = min(nbt, R - b0)
                 check(lib.plsb200_rb_boot_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n, self._p(cs),
-                                              int(cs.numel()) - 1, self._p(pivot), self._p(s1), self._p(s2),
+                                              int(cs.numel()) - 1, int(unit_cells), self._p(pivot), self._p(s1),
+                                              self._p(s2),
                                               self._p(T), self._p(nrm2), self._p(ws), ws.numel(), self._stream()),
                       "rb_boot_f64")
             self._mark("rb_boot")

@@ -116,11 +116,12 @@ def test_na_placeholders_and_no_gpu_work_when_skipped():
     assert res.resample_tests.conf_ints == ["NA", "NA"]
 
 
-def test_unimplemented_methods_fail_loudly():
+def test_unimplemented_paths_fail_loudly():
+    """split-half for the behaviour / multiblock family is not built yet: it must raise, not fall back."""
     import plspy_b200
-    g = _load("mb_full")
+    g = _load("rb_bal")
     with pytest.raises(plspy_b200.exceptions.NotImplementedError):
-        _run_product(g)
+        _run_product(g, num_perm=0, num_boot=0, num_split=3, lv=1)
 
 
 SPLIT_CASES = [c for c in TASK_CASES if int(_load(c)["nsplit"]) > 0]
@@ -199,3 +200,26 @@ def test_rb_matches_oracle_cfg2_shape():
     np.testing.assert_allclose(rt.std_errs, o["boot"]["std_errs"], rtol=1e-8)
     np.testing.assert_allclose(rt.boot_ratios, o["boot"]["boot_ratios"], rtol=1e-8)
     np.testing.assert_allclose(rt.LVcorr, o["boot"]["LVcorr"], rtol=1e-7, atol=1e-9)
+
+
+MB_CASES = [c for c in golden_cases() if c.startswith(("mb", "cmb"))]
+
+
+@pytest.mark.parametrize("name", MB_CASES)
+def test_multiblock_methods_match_reference_golden(name):
+    g = _load(name)
+    res = _run_product(g)
+    rt = res.resample_tests
+    live = np.abs(g["s"]) > 1e-8
+    np.testing.assert_array_equal(rt.perm_debug_dict["indices"], g["perm_idx_task"])
+    np.testing.assert_array_equal(rt.perm_debug_dict["indices_behaviour"], g["perm_idx_beh"])
+    np.testing.assert_array_equal(rt.permute_ratio, g["permute_ratio"])
+    np.testing.assert_array_equal(rt.stepdown_ratio, g["stepdown_ratio"])
+    np.testing.assert_array_equal(rt.boot_debug_dict["indices"], g["boot_idx_task"])
+    np.testing.assert_array_equal(rt.boot_debug_dict["indices_behaviour"], g["boot_idx_beh"])
+    np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], g["boot_ratios"][:, live], rtol=1e-8)
+    np.testing.assert_allclose(rt.LVcorr[:, :, live], g["LVcorr"][:, :, live], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(rt.conf_ints_T[0][:, live], g["conf_T_lo"][:, live], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(rt.conf_ints_T[1][:, live], g["conf_T_hi"][:, live], rtol=1e-7, atol=1e-9)
