@@ -166,6 +166,18 @@ int plsb200_coef_project_f64(const double* C1, int N, int M, const double* d2, c
 int plsb200_rb_lvcorr_f64(const double* T, const double* nrm2, const double* Yz, const int32_t* idx, int N, int nb,
                           int K, int R, const int32_t* cell_start, int ncell, double* LVcorr, void* stream);
 
+/* ---- split-half Gram blocks in p-space (behaviour / multiblock family) -----------------------------
+ * For splits [s0, s0+ns): half h of split s is a list of nmax positions -> data rows `ids[s][h][pos]`, cut
+ * into `ncell` blocks by the position offsets `cells[h][0..ncell]` (the same for every split); rows of
+ * standardised blocks come from Xstd, those of the trailing `unit_cells` blocks from Xlin (both N x p dense).
+ * Q[s][h][pos][k] are the per-position coefficients of the K rows of the half's cross-block matrix.
+ * Output S3[s] = [S11 | S12 | S22] (3 x K x K): M1 M1^T, M1 M2^T, M2 M2^T.  K <= 24.
+ * (split_half_resampling.py:198-262, 315-383, 615-683, 734-802)                                       */
+size_t plsb200_half_gram_f64_workspace(int64_t p, int K, int ns);
+int plsb200_half_gram_f64(const double* Xstd, const double* Xlin, int64_t p, const int32_t* ids, const double* Q,
+                          const int32_t* cells, int ncell, int unit_cells, int nmax, int K, int s0, int ns,
+                          double* S3, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K3: batched symmetric eigensolver, one warp per K x K matrix (K <= 32), one-sided Jacobi with
  * shuffle-based rotations.  Replaces np.linalg.svd of the K x p half-sample cross-block matrices
  * (class_functions.py:122 as called from split_half_resampling.py:194,207,255,311,612-613,...) through

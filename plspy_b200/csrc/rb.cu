@@ -340,9 +340,126 @@ __global__ void __launch_bounds__(256) coef_project_kernel(const double* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-half Gram blocks for the behaviour / multiblock family (split_half_resampling.py:198-262,
+// 315-383, 615-683, 734-802).  Half h of split s is a list of positions -> data rows (ids) cut into
+// blocks; the rows of its cross-block matrix are
+//     M_h[k](v) = sum_c sc_{h,c}(v) sum_{pos in c} x[ids[pos], v] Q_h[pos, k]
+// with sc = 1/(sd sqrt(n)) over the block's member rows for standardised blocks (x from Xstd) and sc = 1 for
+// the trailing `unit_cells` blocks (plain linear rows, x from Xlin: the multiblock task part).
+// CTA = 256 voxels: phase 1 forms both halves' K rows per voxel, phase 2 reduces the three K x K blocks
+// S11, S12, S22 over the tile; partials per (tile, split) are summed in a fixed order afterwards.
+template <int KC>
+__global__ void __launch_bounds__(256) half_gram_kernel(const double* __restrict__ Xstd, const double* __restrict__ Xlin,
+                                                       long long p, const int32_t* __restrict__ ids,
+                                                       const double* __restrict__ Q,
+                                                       const int32_t* __restrict__ cells, int ncell, int unit_cells,
+                                                       int nmax, int K, int s0, int ns, double* __restrict__ part) {
+    extern __shared__ __align__(16) double smh[];
+    double* Rs = smh;                                   // [2][256][KC]
+    double* Qs = Rs + 2 * 256 * KC;                     // [nmax][KC]
+    int* sid = reinterpret_cast<int*>(Qs + (size_t)nmax * KC);   // [nmax]
+    const int tid = threadIdx.x;
+    const long long v = (long long)blockIdx.x * 256 + tid;
+    const bool ok = v < p;
+    for (int ss = 0; ss < ns; ++ss) {
+        const int sp = s0 + ss;
+        for (int h = 0; h < 2; ++h) {
+            __syncthreads();
+            const double* q = Q + ((size_t)(sp * 2 + h) * nmax) * K;
+            for (int i = tid; i < nmax * KC; i += 256) {
+                const int pos = i / KC, k = i % KC;
+                Qs[i] = k < K ? q[(size_t)pos * K + k] : 0.0;
+            }
+            for (int i = tid; i < nmax; i += 256) sid[i] = ids[(size_t)(sp * 2 + h) * nmax + i];
+            __syncthreads();
+            double rows[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) rows[k] = 0.0;
+            const int32_t* cs = cells + h * (ncell + 1);
+            for (int c = 0; c < ncell; ++c) {
+                const int b = cs[c], e = cs[c + 1];
+                const bool unit = c >= ncell - unit_cells;
+                const double* src = unit ? Xlin : Xstd;
+                double m1 = 0.0, m2 = 0.0, P[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) P[k] = 0.0;
+                for (int pos = b; pos < e; ++pos) {
+                    const double x = ok ? __ldg(src + (long long)sid[pos] * p + v) : 0.0;
+                    m1 += x;
+                    m2 = fma(x, x, m2);
+                    const double* qq = Qs + pos * KC;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) P[k] = fma(x, qq[k], P[k]);
+                }
+                const double n = (double)(e - b);
+                m1 /= n; m2 /= n;
+                const double var = m2 - m1 * m1;
+                const double sc = unit ? 1.0 : ((var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * n) : 0.0);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) rows[k] = fma(sc, P[k], rows[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) Rs[(h * 256 + tid) * KC + k] = ok ? rows[k] : 0.0;
+        }
+        __syncthreads();
+        double* out = part + ((size_t)blockIdx.x * ns + ss) * 3 * K * K;
+        for (int o = tid; o < 3 * K * K; o += 256) {
+            const int which = o / (K * K), a = (o % (K * K)) / K, b = o % K;
+            const double* Ra = Rs + (which == 2 ? 256 * KC : 0) + a;
+            const double* Rb = Rs + (which == 0 ? 0 : 256 * KC) + b;
+            double acc = 0.0;
+            for (int t = 0; t < 256; ++t) acc = fma(Ra[t * KC], Rb[t * KC], acc);
+            out[o] = acc;
+        }
+    }
+}
+
 }  // namespace plsb
 
 using namespace plsb;
+
+extern "C" size_t plsb200_half_gram_f64_workspace(int64_t p, int K, int ns) {
+    if (p <= 0 || K <= 0 || ns <= 0) return 0;
+    return (size_t)cdiv(p, 256) * ns * 3 * K * K * sizeof(double);
+}
+
+extern "C" int plsb200_half_gram_f64(const double* Xstd, const double* Xlin, int64_t p, const int32_t* ids,
+                                     const double* Q, const int32_t* cells, int ncell, int unit_cells, int nmax, int K,
+                                     int s0, int ns, double* S3, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    PLSB_CHECK_ARG(Xstd && Xlin && ids && Q && cells && S3 && workspace, "half_gram_f64: null pointer");
+    PLSB_CHECK_ARG(p > 0 && ncell > 0 && nmax > 0 && K > 0 && ns > 0, "half_gram_f64: bad shape");
+    if (K > 24) {
+        set_err("half_gram_f64: K=%d > 24 not supported", K);
+        return PLSB200_EUNSUPPORTED;
+    }
+    const int ntile = (int)cdiv(p, 256);
+    const size_t need = (size_t)ntile * ns * 3 * K * K * sizeof(double);
+    if (workspace_bytes < need) {
+        set_err("half_gram_f64: workspace %zu < %zu bytes", workspace_bytes, need);
+        return PLSB200_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+#define PLSB_HG_LAUNCH(KCV)                                                                                       \
+    do {                                                                                                          \
+        size_t smem = ((size_t)2 * 256 * KCV + (size_t)nmax * KCV) * sizeof(double) + (size_t)nmax * sizeof(int);  \
+        if (smem > 220 * 1024) { set_err("half_gram_f64: halves too large for shared memory"); return PLSB200_EUNSUPPORTED; } \
+        PLSB_CUDA(cudaFuncSetAttribute(half_gram_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        half_gram_kernel<KCV><<<ntile, 256, smem, st>>>(Xstd, Xlin, p, ids, Q, cells, ncell, unit_cells, nmax, K, s0, \
+                                                        ns, (double*)workspace);                                  \
+    } while (0)
+    if (K <= 8) PLSB_HG_LAUNCH(8);
+    else if (K <= 16) PLSB_HG_LAUNCH(16);
+    else PLSB_HG_LAUNCH(24);
+#undef PLSB_HG_LAUNCH
+    PLSB_LAUNCH_CHECK("half_gram_kernel");
+    const long long n = (long long)ns * 3 * K * K;
+    rb_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const double*)workspace, ntile, n,
+                                                             S3 + (size_t)s0 * 3 * K * K);
+    PLSB_LAUNCH_CHECK("rb_reduce_kernel");
+    return PLSB200_OK;
+}
 
 extern "C" int plsb200_scatter_coef_f64(const double* E, int N, int K, const int32_t* idx, int R, double* C,
                                         void* stream) {

@@ -313,9 +313,15 @@ class Engine:
         Y = self.to_device(Y, F64); U = self.to_device(U, F64)
         cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
         idx = self.to_device(idx, I32) if idx is not None else None
-        N, nb = int(Y.shape[0]), int(Y.shape[1])
+        nb = int(Y.shape[1])
+        # number of resampled rows = length of an index vector (half-samples are shorter than Y)
+        N = int(idx.shape[1]) if idx is not None else int(Y.shape[0])
         R = int(idx.shape[0]) if idx is not None else 1
         Kc = int(U.shape[1])
+        if int(cs[-1].item()) != N:
+            raise ValueError(f"rb_coef: blocks cover {int(cs[-1].item())} rows, index vectors have {N}")
+        if scatter and N != int(Y.shape[0]):
+            raise ValueError("rb_coef: scatter mode needs full-length index vectors")
         Q = self._empty(R, N, Kc)
         W = self._empty(R, N) if scatter else None
         Yz = self._empty(R, N, nb) if want_yz else None
@@ -360,3 +366,24 @@ class Engine:
             check(lib.plsb200_rb_lvcorr_f64(self._p(T), self._p(nrm2), self._p(Yz), self._p(idx), N, nb, K, R,
                                             self._p(cs), ncell, self._p(LV), self._stream()), "rb_lvcorr_f64")
         return LV
+
+    def half_gram(self, Xstd, Xlin, ids, Q, cells, unit_cells, max_ws_bytes=256 << 20):
+        """Split-half Gram blocks in p-space: ids (S x 2 x nmax int32), Q (S x 2 x nmax x K),
+        cells (2 x (ncell+1) int32 position offsets).  Returns S3 (S x 3 x K x K) = [S11, S12, S22]."""
+        ids = self.to_device(ids, I32); Q = self.to_device(Q, F64)
+        cells = self.to_device(np.asarray(cells, dtype=np.int32), I32)
+        S, nmax, K = int(ids.shape[0]), int(ids.shape[2]), int(Q.shape[3])
+        ncell = int(cells.shape[1]) - 1
+        p = int(Xstd.shape[1])
+        S3 = self._empty(S, 3, K, K)
+        per = lib.plsb200_half_gram_f64_workspace(p, K, 1)
+        ns = max(1, min(S, int(max_ws_bytes // max(per, 1))))
+        with torch.cuda.device(self.device):
+            ws = self._ws(per * ns)
+            for s0 in range(0, S, ns):
+                n = min(ns, S - s0)
+                check(lib.plsb200_half_gram_f64(self._p(Xstd), self._p(Xlin), p, self._p(ids), self._p(Q),
+                                                self._p(cells), ncell, int(unit_cells), nmax, K, s0, n,
+                                                self._p(S3), self._p(ws), ws.numel(), self._stream()),
+                      "half_gram_f64")
+        return S3

@@ -116,15 +116,7 @@ def test_na_placeholders_and_no_gpu_work_when_skipped():
     assert res.resample_tests.conf_ints == ["NA", "NA"]
 
 
-def test_unimplemented_paths_fail_loudly():
-    """split-half for the behaviour / multiblock family is not built yet: it must raise, not fall back."""
-    import plspy_b200
-    g = _load("rb_bal")
-    with pytest.raises(plspy_b200.exceptions.NotImplementedError):
-        _run_product(g, num_perm=0, num_boot=0, num_split=3, lv=1)
-
-
-SPLIT_CASES = [c for c in TASK_CASES if int(_load(c)["nsplit"]) > 0]
+SPLIT_CASES = [c for c in golden_cases() if int(_load(c)["nsplit"]) > 0]
 
 
 @pytest.mark.parametrize("name", SPLIT_CASES)
@@ -137,7 +129,8 @@ def test_split_half_matches_reference_golden(name):
     tt, sh = res.pls_repro_tt, res.pls_repro_sh
     lvn = int(g["lv"])
     live = np.abs(g["s"]) > 1e-8
-    nl = int(live.sum()) if str(g["method"]) == "mct" else g["tt_pls_s_train"].shape[0]
+    nl = int(live.sum()) if str(g["method"]) in ("mct", "rb", "mb") else g["tt_pls_s_train"].shape[0]
+    nl = min(nl, g["tt_pls_s_train"].shape[0])
     for k in ("pls_s_train", "pls_s_test", "pls_s_train_null", "pls_s_test_null"):
         a, b = tt[k], g["tt_" + k]
         assert a.shape == b.shape, k
