@@ -1,0 +1,314 @@
+// K4 for tall designs (N > 320 rows): row-split variant of boot_moments_kernel.
+//
+// The A fragments of 8 voxels x N rows no longer fit one warp's registers, so RS (2 or 4) warps share a
+// voxel group and each keeps N/RS rows resident.  A pipeline stage is ONE 8-column block of the packed
+// coefficients for all rows (RS*NKS k-steps, <= 82 KB), every warp runs its NKS-long DMMA chain on its own
+// row range, the partial D fragments are exchanged through shared memory (double-buffered, one named
+// barrier per block) and the warp with row-chunk 0 folds (VS - pivot) into the running moments.
+// The accumulator set rotates with the block index modulo NACC = period / 8 columns.
+#include "common.cuh"
+
+namespace plsb {
+
+struct RsPlan {
+    int Kp, nacc, nb, rs, nks, stot, ncb, nstage, nsplit, cb_per_split, vox;
+    size_t stage_doubles, smem_bytes;
+};
+
+static bool rs_plan(int N, int K, int R, int64_t p, RsPlan& b) {
+    if (K < 1 || K > 24 || N <= 320 || R < 1) return false;
+    int best_kp = 0, best_blk = 0;
+    for (int blk = 3; blk >= 1; --blk) {
+        const int cols = 8 * blk;
+        for (int kp = K; kp <= cols; ++kp)
+            if (cols % kp == 0) { if (best_kp == 0 || kp < best_kp) { best_kp = kp; best_blk = blk; } break; }
+    }
+    if (!best_kp) return false;
+    b.Kp = best_kp; b.nacc = best_blk; b.nb = 8 * best_blk / best_kp;
+    const int ksteps = (int)cdiv(N, 4);
+    b.rs = ksteps <= 160 ? 2 : 4;
+    int nks = (int)cdiv(cdiv(ksteps, b.rs), 8) * 8;      // buckets of 8 k-steps: 48, 56, 64, 72, 80
+    if (nks < 48) nks = 48;
+    if (nks > 80) return false;                          // N > 1280
+    b.nks = nks; b.stot = nks * b.rs;
+    b.ncb = (int)cdiv(R, b.nb) * b.nacc;
+    b.stage_doubles = (size_t)b.stot * 32;
+    b.vox = 8 * (8 / b.rs);
+    const size_t extra = (size_t)(8 / b.rs) * 16 * b.Kp * 8 + (size_t)2 * (8 / b.rs) * (b.rs - 1) * 64 * 8 + 256;
+    int ns = (int)((227 * 1024 - extra) / (b.stage_doubles * 8));
+    if (ns > 4) ns = 4;
+    if (ns < 2) return false;
+    b.nstage = ns;
+    b.smem_bytes = ns * b.stage_doubles * 8 + extra;
+    const int64_t tiles = cdiv(p > 0 ? p : 1, b.vox);
+    const int nsm = num_sms();
+    const int nper = b.ncb / b.nacc;
+    int best = 1; double best_cost = 1e30;
+    for (int n = 1; n <= 8; ++n) {
+        if (n > 1 && nper / n < 8) break;
+        const double waves = (double)tiles * n / nsm;
+        const double cost = ceil(waves) / waves + 0.004 * (n - 1);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = n; }
+    }
+    const int per_per_split = (int)cdiv(nper, best);
+    b.cb_per_split = per_per_split * b.nacc;
+    b.nsplit = (int)cdiv(nper, per_per_split);
+    return true;
+}
+
+// packed layout: offset(cb, s, lane) = (cb*stot + s)*32 + lane ; column j = r*Kp + k -> cb = j/8, n = j%8 ;
+// row i -> chunk rc = i / (4*nks), s = rc*nks + (i % (4*nks))/4, q = i%4 ; lane = 4n + q
+__global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restrict__ E, int N, int K,
+                                                          const int32_t* __restrict__ idx, int Kp, int stot,
+                                                          double* __restrict__ coef) {
+    extern __shared__ int ids[];          // E (N x K) stays in global memory: L1/L2-resident, read via __ldg
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double acc[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) acc[k] = 0.0;
+        for (int src = 0; src < N; ++src)
+            if (ids[src] == i) {
+#pragma unroll
+                for (int k = 0; k < 24; ++k)
+                    if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
+            }
+        const int s = i >> 2, q = i & 3;
+#pragma unroll
+        for (int k = 0; k < 24; ++k)
+            if (k < K) {
+                const long long j = (long long)r * Kp + k;
+                coef[((size_t)(j >> 3) * stot + s) * 32 + 4 * (int)(j & 7) + q] = acc[k];
+            }
+    }
+}
+
+template <int NKS, int NACC, int RS>
+__global__ void __launch_bounds__(256, 1)
+boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
+                       const double* __restrict__ coef, int ncb, int cb_per_split, int nstage, int R, int Kp, int K,
+                       const double* __restrict__ pivot, double* __restrict__ osum, double* __restrict__ osumsq) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int NVG = 8 / RS;                    // voxel groups per CTA
+    constexpr int STOT = NKS * RS;
+    constexpr int stage_doubles = STOT * 32;
+    constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
+    double* ring = reinterpret_cast<double*>(smraw);
+    double* red = ring + (size_t)nstage * stage_doubles;                 // [NVG][2][8][Kp]
+    double* exch = red + NVG * 16 * Kp;                                  // [2][NVG][RS-1][32][2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(exch + 2 * NVG * (RS - 1) * 64);
+    uint64_t* empty = full + nstage;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int vg = warp / RS, rc = warp % RS;
+    const int q = lane & 3, vr = lane >> 2;
+    const long long v = (long long)blockIdx.x * (NVG * 8) + vg * 8 + vr;
+    const int cb0 = blockIdx.y * cb_per_split;
+    const int cb1 = min(ncb, cb0 + cb_per_split);
+    const int nit = cb1 - cb0;
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int it, int slot) {
+        mbar_expect_tx(full + slot, stage_bytes);
+        const char* src = reinterpret_cast<const char*>(coef + (size_t)(cb0 + it) * stage_doubles);
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+#pragma unroll 1
+        for (uint32_t off = 0; off < stage_bytes; off += 16384u)
+            bulk_g2s(dst + off, src + off, min(16384u, stage_bytes - off), full + slot);
+    };
+    if (tid == 0)
+        for (int it = 0; it < min(nstage, nit); ++it) issue(it, it);
+
+    double a[NKS];
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        const int row = (rc * NKS + s) * 4 + q;
+        a[s] = (row < N && v < p) ? __ldg(X + (long long)row * ldx + v) : 0.0;
+    }
+    double piv[NACC][2], s1[NACC][2], s2[NACC][2];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = 8 * j + 2 * q + e, k = c % Kp;
+            piv[j][e] = (rc == 0 && pivot != nullptr && k < K && v < p) ? __ldg(pivot + v * K + k) : 0.0;
+            s1[j][e] = 0.0; s2[j][e] = 0.0;
+        }
+    const int nb = 8 * NACC / Kp;
+
+    int slot = 0, prev_slot = 0;
+    uint32_t phase = 0, prev_phase = 0;
+    for (int it0 = 0; it0 < nit; it0 += NACC) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            const int it = it0 + j;
+            if (it >= nit) break;
+            if (tid == 0 && it > 0) {
+                const int nx = it - 1 + nstage;
+                if (nx < nit) {
+                    mbar_wait(empty + prev_slot, prev_phase);
+                    issue(nx, prev_slot);
+                }
+            }
+            __syncwarp();
+            mbar_wait(full + slot, phase);
+            double d0 = -piv[j][0], d1 = -piv[j][1];
+            const volatile double* bs = ring + (size_t)slot * stage_doubles + (size_t)rc * NKS * 32 + lane;
+#pragma unroll
+            for (int s = 0; s < NKS; ++s) {
+                const double b = bs[s * 32];
+                dmma884(d0, d1, a[s], b);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+            // combine the RS partial fragments of this voxel group
+            double* ex = exch + (size_t)((it & 1) * NVG + vg) * (RS - 1) * 64;
+            if (rc > 0) {
+                ex[(rc - 1) * 64 + lane * 2] = d0;
+                ex[(rc - 1) * 64 + lane * 2 + 1] = d1;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + vg), "r"(RS * 32) : "memory");
+            if (rc == 0) {
+#pragma unroll
+                for (int c = 0; c < RS - 1; ++c) { d0 += ex[c * 64 + lane * 2]; d1 += ex[c * 64 + lane * 2 + 1]; }
+                const long long col0 = (long long)(cb0 + it) * 8 + 2 * q;     // flattened (resample, k) column
+                if (col0 / Kp < R) { s1[j][0] += d0; s2[j][0] = fma(d0, d0, s2[j][0]); }
+                if ((col0 + 1) / Kp < R) { s1[j][1] += d1; s2[j][1] = fma(d1, d1, s2[j][1]); }
+            }
+            prev_slot = slot; prev_phase = phase;
+            if (++slot == nstage) { slot = 0; phase ^= 1u; }
+        }
+    }
+    if (rc != 0) return;
+    double* r1 = red + vg * (16 * Kp);
+    double* r2 = r1 + 8 * Kp;
+    for (int i = lane; i < 16 * Kp; i += 32) r1[i] = 0.0;
+    __syncwarp();
+    for (int round = 0; round < nb; ++round) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * j + 2 * q + e;
+                if (c / Kp == round) {
+                    r1[vr * Kp + c % Kp] += s1[j][e];
+                    r2[vr * Kp + c % Kp] += s2[j][e];
+                }
+            }
+        __syncwarp();
+    }
+    const long long vbase = (long long)blockIdx.x * (NVG * 8) + vg * 8;
+    double* o1 = osum + (size_t)blockIdx.y * p * K;
+    double* o2 = osumsq + (size_t)blockIdx.y * p * K;
+    for (int i = lane; i < 8 * K; i += 32) {
+        const int rr = i / K, k = i % K;
+        if (vbase + rr < p) {
+            o1[(vbase + rr) * K + k] = r1[rr * Kp + k];
+            o2[(vbase + rr) * K + k] = r2[rr * Kp + k];
+        }
+    }
+}
+
+__global__ void rs_moments_reduce_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int nsplit,
+                                         long long n, double* __restrict__ sum, double* __restrict__ sumsq) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < nsplit; ++s) { a += p1[(size_t)s * n + i]; b += p2[(size_t)s * n + i]; }
+    sum[i] = a; sumsq[i] = b;
+}
+
+template <int NKS, int NACC, int RS>
+static int rs_launch(const RsPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R,
+                     const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_rs_kernel<NKS, NACC, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)b.smem_bytes));
+    dim3 grid((unsigned)cdiv(p, b.vox), (unsigned)b.nsplit);
+    boot_moments_rs_kernel<NKS, NACC, RS><<<grid, 256, b.smem_bytes, st>>>(X, ldx, N, p, coef, b.ncb, b.cb_per_split,
+                                                                          b.nstage, R, b.Kp, K, pivot, o1, o2);
+    PLSB_LAUNCH_CHECK("boot_moments_rs_kernel");
+    return PLSB200_OK;
+}
+
+template <int NACC, int RS>
+static int rs_dispatch_nks(const RsPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                           int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    switch (b.nks) {
+        case 48: return rs_launch<48, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 56: return rs_launch<56, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 64: return rs_launch<64, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 72: return rs_launch<72, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 80: return rs_launch<80, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        default: set_err("boot_moments_f64: no row-split kernel for nks=%d", b.nks); return PLSB200_EUNSUPPORTED;
+    }
+}
+
+template <int RS>
+static int rs_dispatch_nacc(const RsPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
+                            int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    switch (b.nacc) {
+        case 1: return rs_dispatch_nks<1, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 2: return rs_dispatch_nks<2, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        default: return rs_dispatch_nks<3, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+    }
+}
+
+size_t boot_rs_coef_bytes(int N, int K, int R) {
+    RsPlan b;
+    if (!rs_plan(N, K, R, 1, b)) return 0;
+    return (size_t)b.ncb * b.stage_doubles * sizeof(double);
+}
+
+size_t boot_rs_workspace(int N, int64_t p, int K, int R) {
+    RsPlan b;
+    if (!rs_plan(N, K, R, p, b)) return 0;
+    return b.nsplit > 1 ? (size_t)2 * b.nsplit * p * K * sizeof(double) : 16;
+}
+
+int boot_rs_pack(const double* E, int N, int K, const int32_t* idx, int R, double* coef, cudaStream_t st) {
+    RsPlan b;
+    if (!rs_plan(N, K, R, 1, b)) {
+        set_err("boot_coef_pack_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=1280)", N, K, R);
+        return PLSB200_EUNSUPPORTED;
+    }
+    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.ncb * b.stage_doubles * sizeof(double), st));
+    size_t smem = (size_t)N * sizeof(int);
+    boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.stot, coef);
+    PLSB_LAUNCH_CHECK("boot_rs_pack_kernel");
+    return PLSB200_OK;
+}
+
+int boot_rs_moments(const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R, const double* pivot,
+                    double* sum, double* sumsq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    RsPlan b;
+    if (!rs_plan(N, K, R, p, b)) {
+        set_err("boot_moments_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=1280)", N, K, R);
+        return PLSB200_EUNSUPPORTED;
+    }
+    double *o1 = sum, *o2 = sumsq;
+    if (b.nsplit > 1) {
+        const size_t need = (size_t)2 * b.nsplit * p * K * sizeof(double);
+        if (!workspace || workspace_bytes < need) {
+            set_err("boot_moments_f64: workspace %zu < %zu bytes", workspace_bytes, need);
+            return PLSB200_EWORKSPACE;
+        }
+        o1 = (double*)workspace; o2 = o1 + (size_t)b.nsplit * p * K;
+    }
+    const int rc = b.rs == 2 ? rs_dispatch_nacc<2>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st)
+                             : rs_dispatch_nacc<4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+    if (rc != PLSB200_OK) return rc;
+    if (b.nsplit > 1) {
+        const long long n = (long long)p * K;
+        rs_moments_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(o1, o2, b.nsplit, n, sum, sumsq);
+        PLSB_LAUNCH_CHECK("moments_reduce_kernel");
+    }
+    return PLSB200_OK;
+}
+
+}  // namespace plsb

@@ -55,6 +55,14 @@ inline int num_sms() {
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// row-split bootstrap-moments path for N > 320 (boot_rs.cu), reached through the plsb200_boot_* entry points
+size_t boot_rs_coef_bytes(int N, int K, int R);
+size_t boot_rs_workspace(int N, int64_t p, int K, int R);
+int boot_rs_pack(const double* E, int N, int K, const int32_t* idx, int R, double* coef, cudaStream_t st);
+int boot_rs_moments(const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R,
+                    const double* pivot, double* sum, double* sumsq, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st);
+
 // ---------------------------------------------------------------- device side
 #ifdef __CUDACC__
 

@@ -120,16 +120,16 @@ __global__ void perm_count_kernel(const double* __restrict__ d2, int R, int K, c
 }
 
 // U_hat_r = Lop (Ku x N) . XL[idx_r, :]   one CTA per resample
-__global__ void uhat_kernel(const double* __restrict__ XL, long long xl_stride, int N, int K,
+__global__ void uhat_kernel(const double* __restrict__ XL, long long xl_stride, int N, int K, int ldk, int koff,
                             const double* __restrict__ Lop, int Ku, const int32_t* __restrict__ idx,
                             double* __restrict__ Uhat) {
     extern __shared__ __align__(16) double smu[];
-    double* Xs = smu;   // gathered XL rows [N][K]
+    double* Xs = smu;   // gathered XL rows [N][K] (K = width of this column chunk, ldk = full width)
     const int r = blockIdx.x;
     const double* xl = XL + (size_t)r * xl_stride;       // xl_stride != 0: one latent matrix per resample
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
         const int src = idx ? idx[(size_t)r * N + i / K] : i / K;
-        Xs[i] = xl[(size_t)src * K + i % K];
+        Xs[i] = xl[(size_t)src * ldk + koff + i % K];
     }
     __syncthreads();
     for (int o = threadIdx.x; o < Ku * K; o += blockDim.x) {
@@ -137,7 +137,7 @@ __global__ void uhat_kernel(const double* __restrict__ XL, long long xl_stride, 
         const double* l = Lop + (size_t)c * N;
         double s = 0.0;
         for (int i = 0; i < N; ++i) s = fma(__ldg(l + i), Xs[i * K + k], s);
-        Uhat[((size_t)r * Ku + c) * K + k] = s;
+        Uhat[((size_t)r * Ku + c) * ldk + koff + k] = s;
     }
 }
 
@@ -254,14 +254,19 @@ extern "C" int plsb200_uhat_f64(const double* XL, int64_t xl_stride, int N, int 
     PLSB_CHECK_ARG(XL && Lop && Uhat, "uhat_f64: null pointer");
     PLSB_CHECK_ARG(N > 0 && K > 0 && Ku > 0 && R >= 0, "uhat_f64: bad shape");
     if (R == 0) return PLSB200_OK;
-    size_t smem = (size_t)N * K * sizeof(double);
-    if (smem > 227 * 1024) {
-        set_err("uhat_f64: N*K too large for shared memory");
+    int kc = K;
+    while (kc > 1 && (size_t)N * kc * sizeof(double) > 200 * 1024) kc = (kc + 1) / 2;
+    if ((size_t)N * kc * sizeof(double) > 200 * 1024) {
+        set_err("uhat_f64: N=%d too large for shared memory", N);
         return PLSB200_EUNSUPPORTED;
     }
-    PLSB_CUDA(cudaFuncSetAttribute(uhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uhat_kernel<<<R, 256, smem, (cudaStream_t)stream>>>(XL, xl_stride, N, K, Lop, Ku, idx, Uhat);
-    PLSB_LAUNCH_CHECK("uhat_kernel");
+    for (int k0 = 0; k0 < K; k0 += kc) {       // columns are independent
+        const int kw = K - k0 < kc ? K - k0 : kc;
+        size_t smem = (size_t)N * kw * sizeof(double);
+        PLSB_CUDA(cudaFuncSetAttribute(uhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uhat_kernel<<<R, 256, smem, (cudaStream_t)stream>>>(XL, xl_stride, N, kw, K, k0, Lop, Ku, idx, Uhat);
+        PLSB_LAUNCH_CHECK("uhat_kernel");
+    }
     return PLSB200_OK;
 }
 

@@ -112,10 +112,16 @@ def test_cst_single_contrast_and_cmb():
     _check(o, res)
 
 
-def test_large_n_bootstrap_fails_loudly():
-    """N > 320 rows is outside what the register-resident moments kernel is built for: it must raise."""
+@pytest.mark.parametrize("groups,C", [((60, 60), 3), ((40, 45, 35), 6)])     # N = 360 (2-way row split), 720 (4-way)
+def test_tall_designs_row_split_kernel(groups, C):
+    """N > 320 rows: the A fragments are split over 2 or 4 warps per voxel group (boot_rs.cu)."""
+    o, res = _both("mct", groups, C, 300, nperm=4, nboot=11, seed=8)
+    _check(o, res)
+
+
+def test_too_tall_design_fails_loudly():
     import plspy_b200
     from plspy_b200._lib import PlsB200Error
-    X, _ = _data((60, 60), 3, 64, seed=8)     # N = 360
+    X, _ = _data((220, 220), 3, 64, seed=9)     # N = 1320 > 1280
     with pytest.raises(PlsB200Error):
-        plspy_b200.PLS(X, (60, 60), 3, num_perm=0, num_boot=3, pls_method="mct")
+        plspy_b200.PLS(X, (220, 220), 3, num_perm=0, num_boot=3, pls_method="mct")

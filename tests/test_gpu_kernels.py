@@ -165,12 +165,34 @@ def test_xv_uhat_colstd(torch_cuda):
     np.testing.assert_allclose(eng.colstd(A).cpu().numpy(), A.std(0), rtol=1e-12)
 
 
+@pytest.mark.parametrize("N,p,K,R", [
+    (324, 200, 12, 21),     # RS=2, smallest bucket
+    (600, 130, 12, 40),     # RS=2, nks=80 -> wait 150 k-steps / 2 = 75 -> bucket 80
+    (1200, 100, 24, 7),     # BASELINE cfg 5 row count: RS=4, 3 accumulator sets, nb=1
+    (700, 90, 5, 19),       # RS=4, K padded to 6
+    (1000, 70, 8, 9),       # RS=4, NACC=1... (24-col period, nb=3)
+    (333, 64, 1, 50),       # K=1
+])
+def test_boot_moments_row_split(torch_cuda, N, p, K, R):
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(N, p, K, R, 7 + N + K, True, offset=1.0)
+    pivot = np.random.RandomState(5).standard_normal((p, K))
+    eng = Engine(X)
+    VS = np.stack([X.T @ _scatter(E, idx[r]) for r in range(R)])
+    for pv in (None, pivot):
+        s1, s2 = eng.boot_moments(E, idx, pv)
+        d = VS - (0 if pv is None else pv)
+        scale = np.abs(d).max()
+        np.testing.assert_allclose(s1.cpu().numpy(), d.sum(0), rtol=1e-11, atol=1e-11 * scale * R)
+        np.testing.assert_allclose(s2.cpu().numpy(), (d ** 2).sum(0), rtol=1e-11, atol=1e-11 * scale ** 2 * R)
+
+
 def test_error_reporting(torch_cuda):
     from plspy_b200.engine import Engine
     from plspy_b200._lib import PlsB200Error
-    eng = Engine(np.zeros((400, 10)))
+    eng = Engine(np.zeros((1400, 10)))
     with pytest.raises(PlsB200Error):
-        eng.boot_moments(np.zeros((400, 3)), np.zeros((2, 400), np.int32))   # N > 320 not supported yet
+        eng.boot_moments(np.zeros((1400, 3)), np.zeros((2, 1400), np.int32))   # N > 1280 is not supported
 
 
 @pytest.mark.parametrize("K", [3, 6, 12, 16, 24, 32])
