@@ -111,6 +111,23 @@ int plsb200_boot_moments_f64(const double* X, int N, int64_t p, int64_t ldx, con
                              int R, const double* pivot, double* sum, double* sumsq,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K4 fast mode: the same moments on the tcgen05 tensor cores with the 3xTF32 split ---------------------
+ * (x = xh + xl, c = ch + cl, each TF32-exact; xh.cl + xl.ch + xh.ch accumulated in FP32 in tensor memory, the
+ * moments in FP64).  Relative error of a salience ~1e-6; std_errs / boot_ratios agree with the FP64 path to
+ * ~1e-6 (north-star tolerance for the fast mode: 1e-4).  Any N; 1 <= K <= 24 per call.
+ * tf32_split_x: X -> `ximage` (plsb200_tf32_ximage_bytes), the TF32 hi/lo planes of X laid out as the
+ *   shared-memory tiles the MMA reads; done once per analysis.
+ * boot_coef_pack_tf32: coefficients C_r = scatter(E, idx_r) -> `coef` (plsb200_boot_coef_bytes_tf32).
+ * boot_moments_tf32: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 (p x K each, overwritten).              */
+size_t plsb200_tf32_ximage_bytes(int N, int64_t p);
+int plsb200_tf32_split_x(const double* X, int N, int64_t p, int64_t ldx, void* ximage, void* stream);
+size_t plsb200_boot_coef_bytes_tf32(int N, int K, int R);
+int plsb200_boot_coef_pack_tf32(const double* E, int N, int K, const int32_t* idx, int R, void* coef, void* stream);
+size_t plsb200_boot_moments_tf32_workspace(int N, int64_t p, int K, int R);
+int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, const void* coef, int K, int R,
+                              const double* pivot, double* sum, double* sumsq, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- std_errs / boot_ratios from the moments (bootstrap_permutation.py:695-703) --------------------
  * mean = pivot + sum/R ; std_errs = sqrt(max(sumsq/R - (sum/R)^2, 0)) (population std, ddof = 0);
  * boot_ratios = numer / std_errs  with numer = V*s (no contrast) or V (contrast), p x K.            */

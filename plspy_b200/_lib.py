@@ -55,6 +55,13 @@ SIGNATURES = {
     "plsb200_boot_moments_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "plsb200_boot_moments_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int,
                                          c_double_p, c_double_p, c_double_p, c_void_p, c_size_t, c_void_p]),
+    "plsb200_tf32_ximage_bytes": (c_size_t, [c_int, c_int64]),
+    "plsb200_tf32_split_x": (c_int, [c_double_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "plsb200_boot_coef_bytes_tf32": (c_size_t, [c_int, c_int, c_int]),
+    "plsb200_boot_coef_pack_tf32": (c_int, [c_double_p, c_int, c_int, c_int32_p, c_int, c_void_p, c_void_p]),
+    "plsb200_boot_moments_tf32_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),
+    "plsb200_boot_moments_tf32": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_double_p, c_double_p,
+                                          c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_boot_finalize_f64": (c_int, [c_double_p, c_double_p, c_int64, c_int, c_int64, c_double_p,
                                           c_double_p, c_double_p, c_void_p]),
     "plsb200_colstd_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_void_p]),

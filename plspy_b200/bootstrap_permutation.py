@@ -10,7 +10,8 @@ boot_ratios, [LVcorr], boot_debug_dict, CI`; "NA" placeholders when a test is sk
 
 Extra keyword-only arguments (not in the reference): `perm_indices`, `boot_indices` (index matrices
 generated elsewhere -- each an int array, or a (task, behaviour) tuple for mb/cmb), `engine`
-(an `Engine` that already holds X on the device).
+(an `Engine` that already holds X on the device), `precision` ("fp64" exact mode, or "tf32x3": the
+bootstrap moment GEMM of the task methods on the tcgen05 tensor cores; p-values stay FP64-exact).
 """
 import abc
 
@@ -309,10 +310,11 @@ class _ResampleTestPLS(ResampleTest):
 
     def __init__(self, X, Y, U, s, V, cond_order, mctype, contrast=None, preprocess=None, nperm=1000,
                  nboot=1000, bscan=None, Xbscan=None, Ybscan=None, lvcorrs_orig=None, Tvsc_orig=None,
-                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None):
+                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None, precision="fp64"):
         self.CI = CI
         _log(f"PLS ALG: {self.pls_alg}")
-        eng = engine if engine is not None else (Engine(X) if (nperm > 0 or nboot > 0) else None)
+        eng = engine if engine is not None else (
+            Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
         if nperm > 0:
             self.permute_ratio, self.stepdown_ratio, self.perm_debug_dict = self._permutation_test(

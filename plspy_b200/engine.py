@@ -29,8 +29,17 @@ class Engine:
     (plspy/core/bootstrap_permutation.py:323-452, 537-675).
     """
 
-    def __init__(self, X, device=None):
+    PRECISIONS = ("fp64", "tf32x3")
+
+    def __init__(self, X, device=None, precision="fp64"):
+        """precision: "fp64" (exact mode, FP64 DMMA) or "tf32x3" (fast mode: the bootstrap moment GEMM runs on the
+        tcgen05 tensor cores with the 3xTF32 split; every N-space quantity -- Gram matrix, permutation p-values,
+        Tdistrib, U_hat -- stays FP64)."""
         _require_cuda()
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {self.PRECISIONS}")
+        self.precision = precision
+        self._ximage = None
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.X = self.to_device(X, F64)
         if self.X.dim() != 2:
@@ -204,6 +213,35 @@ class Engine:
 
     KMAX = 24   # columns per boot_moments launch
 
+    @property
+    def ximage(self):
+        """TF32 hi/lo planes of X in the tile order of the tcgen05 kernel (fast mode), built once per engine."""
+        if self._ximage is None:
+            with torch.cuda.device(self.device):
+                img = self._ws(lib.plsb200_tf32_ximage_bytes(self.N, self.p))
+                check(lib.plsb200_tf32_split_x(self._p(self.X), self.N, self.p, self.ldx, self._p(img), self._stream()),
+                      "tf32_split_x")
+            self._ximage = img
+        return self._ximage
+
+    def _boot_moments_tf32(self, E, idx, pivot, R, K):
+        with torch.cuda.device(self.device):
+            nbytes = lib.plsb200_boot_coef_bytes_tf32(self.N, K, R)
+            if nbytes == 0:
+                raise _lib.PlsB200Error(f"boot_moments (tf32x3): unsupported shape N={self.N} K={K} R={R}")
+            img = self.ximage
+            coef = self._ws(nbytes)
+            check(lib.plsb200_boot_coef_pack_tf32(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
+                                                  self._stream()), "boot_coef_pack_tf32")
+            ws = self._ws(lib.plsb200_boot_moments_tf32_workspace(self.N, self.p, K, R))
+            s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
+            self._mark("boot_moments")
+            check(lib.plsb200_boot_moments_tf32(self._p(img), self.N, self.p, self._p(coef), K, R, self._p(pivot),
+                                                self._p(s1), self._p(s2), self._p(ws), ws.numel(), self._stream()),
+                  "boot_moments_tf32")
+            self._mark("boot_moments")
+        return s1, s2
+
     def boot_moments(self, E, idx, pivot=None):
         """K4: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 with VS_r = X^T scatter(E, idx_r); p x K each."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)
@@ -217,6 +255,8 @@ class Engine:
                 parts.append(self.boot_moments(E[:, sl].contiguous(), idx,
                                                None if pivot is None else pivot[:, sl].contiguous()))
             return torch.cat([a for a, _ in parts], dim=1), torch.cat([b for _, b in parts], dim=1)
+        if self.precision == "tf32x3":
+            return self._boot_moments_tf32(E, idx, pivot, R, K)
         with torch.cuda.device(self.device):
             nbytes = lib.plsb200_boot_coef_bytes(self.N, K, R)
             if nbytes == 0:

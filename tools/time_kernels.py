@@ -47,3 +47,21 @@ t = timeit(lambda: _lib.check(_lib.lib.plsb200_boot_moments_f64(X.data_ptr(), a.
 out["boot_moments_ms"] = t; out["boot_moments_tflops"] = 2.0 * a.p * a.N * K * R / t * 1e-9
 out["boot_ws_mb"] = wsb / 1e6
 print(json.dumps(out, indent=1))
+
+# ---- fast mode (3xTF32 on tcgen05): split, pack, moments
+L_ = _lib.lib
+img = torch.empty(L_.plsb200_tf32_ximage_bytes(a.N, a.p), dtype=torch.uint8, device="cuda")
+t = timeit(lambda: _lib.check(L_.plsb200_tf32_split_x(X.data_ptr(), a.N, a.p, a.p, img.data_ptr(), st), "split"))
+out["tf32_split_x_ms"] = t; out["tf32_split_x_gbs"] = (a.N * a.p * 8 + img.numel()) / t * 1e-6
+cb = L_.plsb200_boot_coef_bytes_tf32(a.N, K, R)
+coef32 = torch.empty(cb, dtype=torch.uint8, device="cuda")
+t = timeit(lambda: _lib.check(L_.plsb200_boot_coef_pack_tf32(E.data_ptr(), a.N, K, idx.data_ptr(), R, coef32.data_ptr(), st), "pack32"))
+out["tf32_coef_pack_ms"] = t; out["tf32_coef_mb"] = cb / 1e6
+wsb = L_.plsb200_boot_moments_tf32_workspace(a.N, a.p, K, R)
+ws32 = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
+t1 = torch.empty(a.p, K, dtype=torch.float64, device="cuda"); t2 = torch.empty_like(t1)
+t = timeit(lambda: _lib.check(L_.plsb200_boot_moments_tf32(img.data_ptr(), a.N, a.p, coef32.data_ptr(), K, R, piv.data_ptr(), t1.data_ptr(), t2.data_ptr(), ws32.data_ptr(), ws32.numel(), st), "mom32"))
+out["tf32_boot_moments_ms"] = t; out["tf32_boot_moments_eff_tflops"] = 2.0 * a.p * a.N * K * R / t * 1e-9
+out["tf32_vs_fp64_max_rel_err_sum"] = float(((t1 - s1).abs().max() / s1.abs().max()).item())
+out["tf32_vs_fp64_max_rel_err_sumsq"] = float(((t2 - s2).abs() / s2.abs()).max().item())
+print(json.dumps(out, indent=1))
