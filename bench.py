@@ -56,7 +56,91 @@ def workload_name(groups, C, p, nperm, nboot):
 
 
 # ------------------------------------------------------------------------------------------------
-def clock_sampler_start(gpu_index):
+class ClockSampler:
+    """Samples SM clock, power and clock-event reasons of one GPU from a thread of this process through NVML
+    (nvidia_ml_py) every `period` seconds.  An external `nvidia-smi -lms` process was measurably disturbing the
+    timed region (its start-up holds the driver for tens of ms), so it is only the fallback when NVML cannot be
+    loaded; in that case it is started well before the timed region."""
+
+    NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+             ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+             ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
+
+    def __init__(self, gpu_index, period=0.05):
+        import threading
+        self.rows, self.period, self._stop, self._on = [], period, threading.Event(), threading.Event()
+        self.nv = self.h = self.proc = self.path = None
+        self.gpu_index = gpu_index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index) if bus is None else self._by_bus(pynvml, gpu_index, bus)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.nv = None
+            self.proc, self.path = _smi_start(gpu_index)
+            time.sleep(1.0)
+
+    @staticmethod
+    def _by_bus(nv, idx, bus):
+        for i in range(nv.nvmlDeviceGetCount()):
+            h = nv.nvmlDeviceGetHandleByIndex(i)
+            if nv.nvmlDeviceGetPciInfo(h).bus == bus:
+                return h
+        return nv.nvmlDeviceGetHandleByIndex(idx)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._on.is_set():
+                try:
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                      nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                      int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+                except Exception:  # noqa: BLE001
+                    pass
+            self._stop.wait(self.period)
+
+    def begin(self):
+        if self.nv is None and self.proc is None:
+            self.proc, self.path = _smi_start(self.gpu_index)
+            time.sleep(1.0)
+        self.rows.clear()
+        self._on.set()
+
+    def end(self):
+        self._on.clear()
+        if self.nv is None:
+            out = _smi_stop(self.proc, self.path)
+            self.proc = None
+            return out
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "source": "nvml in-process, 50 ms period"}
+        rows = list(self.rows)
+        if rows:
+            pmax = max(r[1] for r in rows)
+            busy = [r[0] for r in rows if r[1] > 0.5 * pmax] or [r[0] for r in rows]
+            out["sm_mhz"] = statistics.median(busy)
+            out["power_w_max"] = pmax
+            out["samples"] = len(rows)
+            for name, attr in self.NAMES:
+                bit = getattr(self.nv, attr, 0)
+                if any(r[2] & bit for r in rows):
+                    out["reasons"].append(name)
+        return out
+
+    def close(self):
+        self._stop.set()
+
+
+def _smi_start(gpu_index):
     f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,8 +153,8 @@ def clock_sampler_start(gpu_index):
     return pr, f.name
 
 
-def clock_sampler_stop(pr, path):
-    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+def _smi_stop(pr, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "source": "nvidia-smi -lms 100"}
     if pr is not None:
         pr.terminate()
         try:
@@ -201,8 +285,8 @@ def run_gpu(args):
     Xd, Vd, gpd, gbd = Xh.to(dev), Vh.to(dev), gph.to(dev), gbh.to(dev)
     torch.cuda.synchronize()
 
-    def one_pass(Xa, Va, pa, ba, events=None):
-        eng = Engine(Xa, device=dev)            # Gram recomputed every step
+    def one_pass(Xa, Va, pa, ba, events=None, precision="fp64"):
+        eng = Engine(Xa, device=dev, precision=precision)            # Gram (and TF32 planes) recomputed every step
         eng.kernel_events = events
         rt = bp.ResampleTest._create("mct", Xa, None, U, s.copy(), Va, co, MCTYPE, preprocess=cf._mean_centre,
                                      nperm=nperm * world, nboot=nboot * world, Tvsc_orig=Tvsc, CI=0.95,
@@ -214,48 +298,62 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_log = {}
+
+    def timed(fn, steps, tag=None):
         sync_all()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()
         sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if tag is not None:
+            step_log[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 3) for i in range(steps)]
+        ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- value arm: inputs resident in HBM
-    for _ in range(args.warmup):
-        one_pass(Xd, Vd, gpd, gbd)
-    events = {}
-    engines = []
-    launches0 = _lib.launch_count()
-    sampler, spath = clock_sampler_start(local) if rank == 0 else (None, None)
-    total_ms = timed(lambda: engines.append(one_pass(Xd, Vd, gpd, gbd, events)[0]), args.steps)
-    clocks = clock_sampler_stop(sampler, spath) if rank == 0 else None
-    launches = _lib.launch_count() - launches0
-    ms_step = total_ms / args.steps
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    def measure(precision):
+        """value arm (inputs resident in HBM) and e2e arm (pinned host buffers in, host results out) for one
+        precision mode; returns a dict of raw timings."""
+        for _ in range(args.warmup):
+            one_pass(Xd, Vd, gpd, gbd, precision=precision)
+        events = {}
+        keep = {}
+        launches0 = _lib.launch_count()
+        if sampler is not None:
+            sampler.begin()
+        # (only the last engine is kept alive: retaining all of them makes every step allocate fresh device memory,
+        # and driver allocations that collide with the clock sampler's NVML queries stall for tens of ms)
+        total_ms = timed(lambda: keep.__setitem__("eng", one_pass(Xd, Vd, gpd, gbd, events, precision)[0]), args.steps,
+                         f"value_{precision}")
+        clocks = sampler.end() if sampler is not None else None
+        launches = _lib.launch_count() - launches0
+        kms = keep["eng"].kernel_ms("boot_moments") if keep else []
+        keep.clear()
+        last = {}
+
+        def e2e_step():
+            # X, V and the index matrices start in pinned host memory; the engine uploads X and V and, of the
+            # global index matrices, only the rows of this rank's shard
+            last["rt"] = one_pass(Xh, Vh, gph, gbh, precision=precision)[1]
+        for _ in range(2):
+            e2e_step()
+        e2e_ms = timed(e2e_step, args.steps, f"e2e_{precision}") / args.steps
+        return {"ms_step": total_ms / args.steps, "kern_ms": sum(kms) / len(kms) if kms else float("nan"),
+                "launches": launches, "clocks": clocks, "e2e_ms": e2e_ms, "rt": last["rt"]}
+
     units_step = (nperm + nboot) * world
-    value = units_step / (ms_step * 1e-3)
-    kms = engines[0].kernel_ms("boot_moments") if engines else []
-    kern_ms = sum(kms) / len(kms) if kms else float("nan")
-    engines.clear()
-
-    # ---- e2e arm: pinned host buffers in, host results out, copies inside the timed region
     h2d = Xh.numel() * 8 + Vh.numel() * 8 + idx_p.nbytes + idx_b.nbytes
-    last = {}
-
-    def e2e_step():
-        # X, V and the index matrices start in pinned host memory; the engine uploads X and V and, of the
-        # global index matrices, only the rows of this rank's shard
-        last["rt"] = one_pass(Xh, Vh, gph, gbh)[1]
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
-    rt = last["rt"]
+    main = measure(args.precision)
+    fast = measure("tf32x3") if (args.precision == "fp64" and not args.no_fast_mode) else None
+    ms_step, kern_ms, launches, clocks, e2e_ms, rt = (main[k] for k in ("ms_step", "kern_ms", "launches", "clocks",
+                                                                        "e2e_ms", "rt"))
+    value = units_step / (ms_step * 1e-3)
     d2h = (rt.std_errs.nbytes + rt.boot_ratios.nbytes + rt.conf_ints[0].nbytes * 2 + rt.permute_ratio.nbytes * 2
            + rt.perm_debug_dict["s_list"].nbytes + rt.boot_debug_dict["left_sv_sampled"].nbytes
            + rt.boot_debug_dict["Tdistrib"].nbytes)
@@ -268,27 +366,56 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (boot_moments_kernel: FP64 DMMA tensor path)
+    # ---- roofline of the dominant kernel (bootstrap moment GEMM)
     flops = 2.0 * p * N * U.shape[1] * nboot          # F_boot = 2 p N K per bootstrap
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
-    peak = float(peaks.get("fp64_cublas_dgemm_tflops", 35.47))
-    achieved = flops / (kern_ms * 1e-3) * 1e-12
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_boot_moments.json"))).get("dram_bytes_per_launch")
-    except Exception:  # noqa: BLE001
-        pass
-    roofline = {
-        "kernel": "boot_moments_kernel<76,3> (FP64 DMMA.8x8x4, A-fragments register-resident, TMA-bulk-fed B)", "bound": "tensor", "achieved": achieved, "peak": peak,
-        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/FP64_PEAKS.json); "
-                       "MEASURED_PEAKS.json carries no FP64 figure",
-        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step, "flops_per_launch": flops,
-    }
+
+    def roofline_of(precision, kern_ms, ms_step):
+        achieved = flops / (kern_ms * 1e-3) * 1e-12
+        if precision == "fp64":
+            peak = float(peaks.get("fp64_cublas_dgemm_tflops", 35.47))
+            kernel = "boot_moments_kernel<76,3> (FP64 DMMA.8x8x4, A-fragments register-resident, TMA-bulk-fed B)"
+            src = ("cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/FP64_PEAKS.json); "
+                   "MEASURED_PEAKS.json carries no FP64 figure")
+            prof = "ncu_boot_moments.json"
+        else:
+            peak = float(peaks.get("tf32_cublas_tflops", 741.7)) / 3.0
+            kernel = ("boot_moments_tf32_kernel<12> (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators, "
+                      "bulk-copy-fed SWIZZLE_64B tiles, FP64 moment epilogue)")
+            src = ("cuBLAS TF32 GEMM 8192^3 measured on this pool's B200 (profiles/FP64_PEAKS.json) / 3: three "
+                   "TF32 MMAs per algorithmic FMA; nominal dense TF32 peak / 3 would be 376 TFLOP/s")
+            prof = "ncu_boot_moments_tf32.json"
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", prof))).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        return {"kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": src, "kernel_ms": kern_ms,
+                "kernel_share_of_step": kern_ms / ms_step, "flops_per_launch": flops}
+
+    roofline = roofline_of(args.precision, kern_ms, ms_step)
+    fast_mode = None
+    if fast is not None:
+        frt = fast["rt"]
+        live = np.abs(s) > 1e-8
+        fast_mode = {
+            "precision_mode": "tf32x3 (bootstrap moment GEMM on tcgen05; Gram, permutations, Tdistrib, U_hat stay FP64)",
+            "value": units_step / (fast["ms_step"] * 1e-3), "unit": UNIT, "ms_per_step": fast["ms_step"],
+            "e2e": {"value": units_step / (fast["e2e_ms"] * 1e-3), "unit": UNIT, "ms_per_step": fast["e2e_ms"],
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(fast["launches"]), "clocks": fast["clocks"],
+            "roofline": roofline_of("tf32x3", fast["kern_ms"], fast["ms_step"]),
+            "vs_fp64_mode": {
+                "permute_ratio_equal": bool(np.array_equal(frt.permute_ratio, rt.permute_ratio)),
+                "boot_ratios_max_rel_diff": float(np.nanmax(np.abs(frt.boot_ratios[:, live] / rt.boot_ratios[:, live] - 1))),
+                "std_errs_max_rel_diff": float(np.nanmax(np.abs(frt.std_errs[:, live] / rt.std_errs[:, live] - 1))),
+                "tolerance": "north star: bootstrap ratios within 1e-4"},
+        }
 
     # ---- CPU baseline: bounded sample of the same workload on the host cores (N=1 only)
     cpu = None
@@ -299,17 +426,19 @@ def run_gpu(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.precision == "fp64" else "tf32x3", "data": "synthetic",
         "config": {"workload": workload_name(GROUPS, C, p, nperm, nboot), "parallelism": f"resample-dp{world}",
                    "l2": "inputs larger than L2 (X 480 MB + packed coefficients 146 MB), no explicit flush",
-                   "precision_mode": "fp64 exact"},
+                   "precision_mode": "fp64 exact" if args.precision == "fp64" else "tf32x3 fast mode"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "fast_mode": fast_mode,
+        "step_ms": step_log,
         "check": {"permute_ratio_lv0": float(rt.permute_ratio[0]), "boot_ratio_max": float(np.nanmax(np.abs(rt.boot_ratios[:, 0])))},
     }
     print(json.dumps(line))
@@ -328,6 +457,9 @@ def main():
     ap.add_argument("--boots", type=int, default=NBOOT)
     ap.add_argument("--ref-sample", type=int, default=6, help="perms and boots per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32x3"],
+                    help="fp64 = exact mode (headline); tf32x3 = fast mode only")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra fast-mode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

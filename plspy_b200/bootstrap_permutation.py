@@ -316,10 +316,13 @@ class _ResampleTestPLS(ResampleTest):
         eng = engine if engine is not None else (
             Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
+        perm_pending = None
         if nperm > 0:
-            self.permute_ratio, self.stepdown_ratio, self.perm_debug_dict = self._permutation_test(
+            # the permutation kernels and their device->host copies are enqueued here; the host only waits for
+            # them after the bootstrap work has been enqueued too, so the GPU never idles between the two tests
+            perm_pending = self._permutation_test(
                 X, Y, U, s, V, cond_order, mctype, nperm, self.pls_alg, preprocess=preprocess, contrast=contrast,
-                bscan=bscan, Xbscan=Xbscan, Ybscan=Ybscan, indices=perm_indices, engine=eng)
+                bscan=bscan, Xbscan=Xbscan, Ybscan=Ybscan, indices=perm_indices, engine=eng, _defer=True)
         else:
             self.permute_ratio = "NA"
             self.stepdown_ratio = "NA"
@@ -339,17 +342,22 @@ class _ResampleTestPLS(ResampleTest):
             self.conf_ints = ["NA", "NA"]
             self.std_errs = "NA"
             self.boot_ratios = "NA"
+        if perm_pending is not None:
+            self.permute_ratio, self.stepdown_ratio, self.perm_debug_dict = perm_pending()
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def _permutation_test(X, Y, U, s, V, cond_order, mctype, niter, pls_alg, preprocess=None, contrast=None,
-                          threshold=1e-12, bscan=None, Xbscan=None, Ybscan=None, indices=None, engine=None):
-        """bootstrap_permutation.py:265-464.  `s` is thresholded in place like the reference (:295)."""
+                          threshold=1e-12, bscan=None, Xbscan=None, Ybscan=None, indices=None, engine=None,
+                          _defer=False):
+        """bootstrap_permutation.py:265-464.  `s` is thresholded in place like the reference (:295).
+        `_defer=True` returns a function that waits for the device results and builds the outputs."""
         eng = engine if engine is not None else Engine(X)
         s[np.abs(s) < threshold] = 0
         if pls_alg in ("mb", "cmb"):
-            return _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan,
-                                    Ybscan, indices)
+            out = _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan,
+                                   Ybscan, indices)
+            return (lambda: out) if _defer else out
         org_s = np.copy(s)
         totcov_org = _stepdown_tail(org_s)
         behaviour = pls_alg in ("rb", "csb")
@@ -377,16 +385,7 @@ class _ResampleTestPLS(ResampleTest):
         counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg in ("mct", "rb") else 0.0)
         dist.allreduce_sum_(counts)
         s_hat = dist.gather_rows(s_hat, niter, lo)
-        counts, s_list = eng.to_host(counts, s_hat)
-        counts = counts.astype(float)
-        permute_ratio = counts[:K] / (niter + 1)
-        stepdown_ratio = counts[K:] / (niter + 1)
-        _log(f"real s: {s}\nratio: {permute_ratio}\nStepdown perm ratio: {stepdown_ratio}")
-
-        debug = _LazyDebugDict()
-        debug["s_list"] = s_list                               # row i = s_hat of permutation i (:439-441)
-        debug["sum_perm"] = np.sum(s_list ** 2, axis=1)        # key names swapped in the reference (:459-460)
-        debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
+        fetch = eng.to_host_async(counts, s_hat)
 
         def _sum_sq_crossblock():                              # sum(permuted**2) (:399): trace(Lop S G S^T Lop^T)
             if Lop is None:
@@ -395,8 +394,20 @@ class _ResampleTestPLS(ResampleTest):
                 raise RuntimeError("perm_debug_dict['sum_s'] is only available in single-process runs")
             d2f, _ = eng.nspace(np.ascontiguousarray(Lop.T), _index_shard(eng, indices, niter, 0, niter))
             return d2f.sum(dim=1).cpu().numpy()
-        debug.set_lazy("sum_s", _sum_sq_crossblock)
-        return permute_ratio, stepdown_ratio, debug
+
+        def finish():
+            counts_h, s_list = fetch()
+            counts_h = counts_h.astype(float)
+            permute_ratio = counts_h[:K] / (niter + 1)
+            stepdown_ratio = counts_h[K:] / (niter + 1)
+            _log(f"real s: {s}\nratio: {permute_ratio}\nStepdown perm ratio: {stepdown_ratio}")
+            debug = _LazyDebugDict()
+            debug["s_list"] = s_list                               # row i = s_hat of permutation i (:439-441)
+            debug["sum_perm"] = np.sum(s_list ** 2, axis=1)        # key names swapped in the reference (:459-460)
+            debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
+            debug.set_lazy("sum_s", _sum_sq_crossblock)
+            return permute_ratio, stepdown_ratio, debug
+        return finish if _defer else finish()
 
     # ------------------------------------------------------------------------------------------
     @staticmethod

@@ -333,37 +333,57 @@ __global__ void __launch_bounds__(128) salience_kernel(const double* __restrict_
     }
 }
 
-// XL = X . V : each CTA takes a voxel chunk, V chunk staged in smem, one warp per row of X.
-constexpr int XV_CHUNK = 1024;
+// XL = X . V : each CTA takes a chunk of XV_CHUNK voxels; the V chunk is staged transposed in shared memory
+// ([k][voxel]: conflict-free), a warp owns XV_RG rows at a time so that every V value fetched from shared
+// memory feeds XV_RG FMAs, lanes stride over the voxels (coalesced 256-B row segments of X), and the per-lane
+// partial sums are combined by shuffles in a fixed order (deterministic).  HBM-bound: X is read once.
+constexpr int XV_CHUNK = 512;
+constexpr int XV_RG = 4;
 template <int KT>
 __global__ void __launch_bounds__(256) xv_partial_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
                                                         const double* __restrict__ V, int K,
                                                         double* __restrict__ part) {
-    extern __shared__ __align__(16) double smv[];   // [XV_CHUNK][K]
+    extern __shared__ __align__(16) double smv[];   // [KT][XV_CHUNK]
     const long long v0 = (long long)blockIdx.x * XV_CHUNK;
     const int nv = (int)min((long long)XV_CHUNK, p - v0);
-    for (int i = threadIdx.x; i < nv * K; i += blockDim.x) smv[i] = V[v0 * K + i];
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int row = warp; row < N; row += nw) {
-        const double* x = X + (long long)row * ldx + v0;
-        for (int k0 = 0; k0 < K; k0 += KT) {
-            double acc[KT];
+    for (int k0 = 0; k0 < K; k0 += KT) {
+        const int kn = min(KT, K - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < XV_CHUNK * KT; i += blockDim.x) {
+            const int c = i / KT, t = i % KT;
+            smv[t * XV_CHUNK + c] = (c < nv && t < kn) ? V[(v0 + c) * K + k0 + t] : 0.0;
+        }
+        __syncthreads();
+        for (int r0 = warp * XV_RG; r0 < N; r0 += nw * XV_RG) {
+            double acc[XV_RG][KT];
 #pragma unroll
-            for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+            for (int r = 0; r < XV_RG; ++r)
+#pragma unroll
+                for (int t = 0; t < KT; ++t) acc[r][t] = 0.0;
+            const double* x = X + (long long)r0 * ldx + v0;
+#pragma unroll 2
             for (int c = lane; c < nv; c += 32) {
-                const double xv = __ldg(x + c);
+                double xr[XV_RG];
 #pragma unroll
-                for (int t = 0; t < KT; ++t)
-                    if (k0 + t < K) acc[t] = fma(xv, smv[c * K + k0 + t], acc[t]);
+                for (int r = 0; r < XV_RG; ++r) xr[r] = (r0 + r < N) ? __ldg(x + (long long)r * ldx + c) : 0.0;
+#pragma unroll
+                for (int t = 0; t < KT; ++t) {
+                    const double vv = smv[t * XV_CHUNK + c];
+#pragma unroll
+                    for (int r = 0; r < XV_RG; ++r) acc[r][t] = fma(xr[r], vv, acc[r][t]);
+                }
             }
 #pragma unroll
-            for (int t = 0; t < KT; ++t) {
-                double s = acc[t];
+            for (int r = 0; r < XV_RG; ++r)
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0 && k0 + t < K) part[((size_t)blockIdx.x * N + row) * K + k0 + t] = s;
-            }
+                for (int t = 0; t < KT; ++t) {
+                    double sacc = acc[r][t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (lane == 0 && r0 + r < N && t < kn)
+                        part[((size_t)blockIdx.x * N + r0 + r) * K + k0 + t] = sacc;
+                }
         }
     }
 }
@@ -522,11 +542,7 @@ extern "C" int plsb200_xv_f64(const double* X, int N, int64_t p, int64_t ldx, co
         set_err("xv_f64: workspace %zu < %zu bytes", workspace_bytes, need);
         return PLSB200_EWORKSPACE;
     }
-    size_t smem = (size_t)XV_CHUNK * K * sizeof(double);
-    if (smem > 200 * 1024) {
-        set_err("xv_f64: K=%d too large", K);
-        return PLSB200_EUNSUPPORTED;
-    }
+    size_t smem = (size_t)XV_CHUNK * 12 * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
     PLSB_CUDA(cudaFuncSetAttribute(xv_partial_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     xv_partial_kernel<12><<<nchunk, 256, smem, st>>>(X, N, p, ldx, V, K, (double*)workspace);

@@ -18,6 +18,7 @@
 //   * persistent CTAs, one per SM; work unit = (voxel tile, contiguous range of column tiles); units are ordered
 //     so that CTAs running concurrently stream the same coefficient range (L2-resident).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace plsb {
 
@@ -29,7 +30,8 @@ constexpr uint32_t TF_A_STAGE = 2 * TF_A_PLANE;        // hi + lo
 
 struct TfPlan {
     int Kp, period, ntile, nres, nkb, nct, nstage, nsplit, ct_per_split, nks_last;
-    int64_t nvt;
+    int cg;            // CTAs per MMA group: 2 = CTA pairs (cta_group::2, UMMA M = 256), 1 = single CTA
+    int64_t nvt;       // voxel-tile groups (tiles / cg, the last group zero-padded)
     uint32_t b_plane, stage_bytes;
     size_t smem_bytes;
 };
@@ -49,14 +51,16 @@ static bool tf_plan(int N, int K, int R, int64_t p, TfPlan& t) {
     t.nks_last = (int)cdiv(N - TF_KB * (t.nkb - 1), 8);
     t.nct = (int)cdiv(R, t.nres);
     t.b_plane = (uint32_t)t.ntile * TF_KB * 4;
-    t.stage_bytes = TF_A_STAGE + 2 * t.b_plane;
+    const char* env = getenv("PLSB200_TF32_CTA_GROUP");
+    t.cg = (env && env[0] == '1') ? 1 : 2;
+    t.stage_bytes = TF_A_STAGE + 2 * t.b_plane / t.cg;
     int ns = (int)((227 * 1024 - 2048) / t.stage_bytes);
-    if (ns > 6) ns = 6;
+    if (ns > 8) ns = 8;
     if (ns < 2) return false;
     t.nstage = ns;
     t.smem_bytes = (size_t)ns * t.stage_bytes + 1024 + 256;
-    t.nvt = cdiv(p > 0 ? p : 1, TF_MV);
-    const int nsm = num_sms();
+    t.nvt = cdiv(cdiv(p > 0 ? p : 1, TF_MV), t.cg);
+    const int nsm = num_sms() / t.cg;
     int best = 1; double best_cost = 1e30;
     for (int n = 1; n <= 8; ++n) {
         if (n > 1 && t.nct / n < 4) break;
@@ -107,47 +111,70 @@ __global__ void __launch_bounds__(TF_MV) split_x_tf32_kernel(const double* __res
 }
 
 // coefficients C_r = scatter(E, idx_r) -> image [column tile][k-block][hi|lo][ntile columns x 16 rows] (same
-// swizzled order, column n = (r % nres)*Kp + k).  One CTA per resample; thread j gathers target row j in index
-// order (deterministic).  The image is zeroed beforehand (padding rows / columns / k >= K).
-__global__ void __launch_bounds__(256) coef_pack_tf32_kernel(const double* __restrict__ E, int N, int K,
-                                                            const int32_t* __restrict__ idx, int Kp, int nres, int ntile,
-                                                            int nkb, int stage_e, float* __restrict__ img) {
+// swizzled order, column n = (r % nres)*Kp + k).  One CTA per resample; 256 target rows (16 k-blocks) per pass:
+// thread j gathers target row j in index order (deterministic), the hi/lo planes of the pass are assembled in
+// shared memory in image order and written out as contiguous K*64-byte runs.  The image is zeroed beforehand
+// (padding rows / columns / k >= K).
+constexpr int CP_ROWS = 256;                       // target rows per pass
+constexpr int CP_KB = CP_ROWS / TF_KB;             // k-blocks per pass
+__global__ void __launch_bounds__(CP_ROWS) coef_pack_tf32_kernel(const double* __restrict__ E, int N, int K,
+                                                                const int32_t* __restrict__ idx, int Kp, int nres,
+                                                                int ntile, int nkb, int stage_e,
+                                                                float* __restrict__ img) {
     extern __shared__ __align__(16) double smp[];
-    int* ids = reinterpret_cast<int*>(smp);
-    double* Esm = smp + (N + 1) / 2;
+    float* stg = reinterpret_cast<float*>(smp);                       // [2 planes][CP_KB][K][16]
+    int* ids = reinterpret_cast<int*>(stg + 2 * CP_KB * K * TF_KB);   // [N]
+    double* Esm = reinterpret_cast<double*>(ids + ((N + 1) & ~1));
     const double* Es = stage_e ? Esm : E;           // tall designs: E stays in global memory (L2-resident)
-    const int r = blockIdx.x;
+    const int r = blockIdx.x, tid = threadIdx.x;
     const int32_t* my = idx + (size_t)r * N;
     if (stage_e)
-        for (int i = threadIdx.x; i < N * K; i += blockDim.x) Esm[i] = E[i];
-    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = my[i];
+        for (int i = tid; i < N * K; i += CP_ROWS) Esm[i] = E[i];
+    for (int i = tid; i < N; i += CP_ROWS) ids[i] = my[i];
     __syncthreads();
     const int ct = r / nres, nbase = (r % nres) * Kp;
     const size_t plane = (size_t)ntile * TF_KB;      // floats
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const int pstride = CP_KB * K * TF_KB;           // floats per staged plane
+    for (int j0 = 0; j0 < N; j0 += CP_ROWS) {
+        const int j = j0 + tid;
         double acc[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc[k] = 0.0;
-        for (int src = 0; src < N; ++src) {
-            if (ids[src] == j) {
+        if (j < N) {
+            for (int src = 0; src < N; ++src) {
+                if (ids[src] == j) {
 #pragma unroll
-                for (int k = 0; k < 24; ++k)
-                    if (k < K) acc[k] += Es[src * K + k];
+                    for (int k = 0; k < 24; ++k)
+                        if (k < K) acc[k] += Es[src * K + k];
+                }
             }
         }
-        const int kb = j / TF_KB, jj = j % TF_KB;
-        float* base = img + ((size_t)ct * nkb + kb) * (2 * plane);
+        const int kbl = tid / TF_KB, jj = tid % TF_KB;
 #pragma unroll
         for (int k = 0; k < 24; ++k) {
             if (k < K) {
                 const int n = nbase + k;
-                const int off = n * 16 + (((jj >> 2) ^ ((n >> 1) & 3)) << 2) + (jj & 3);
+                const int off = (kbl * K + k) * TF_KB + (((jj >> 2) ^ ((n >> 1) & 3)) << 2) + (jj & 3);
                 float h, l;
                 split_tf32(acc[k], h, l);
-                base[off] = h;
-                base[plane + off] = l;
+                stg[off] = h;
+                stg[pstride + off] = l;
             }
         }
+        __syncthreads();
+        // copy out: (plane, k-block) -> one contiguous run of K*16 floats
+        const int kb0 = j0 / TF_KB;
+        const int run4 = K * TF_KB / 4;              // float4 per run
+        for (int i = tid; i < 2 * CP_KB * run4; i += CP_ROWS) {
+            const int q = i % run4, kbl2 = (i / run4) % CP_KB, h = i / (run4 * CP_KB);
+            const int kb = kb0 + kbl2;
+            if (kb < nkb) {
+                const float4 val = *reinterpret_cast<const float4*>(stg + h * pstride + kbl2 * K * TF_KB + 4 * q);
+                float* dst = img + ((size_t)ct * nkb + kb) * (2 * plane) + h * plane + (size_t)nbase * TF_KB + 4 * q;
+                *reinterpret_cast<float4*>(dst) = val;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -191,7 +218,64 @@ struct TfArgs {
     uint32_t b_plane, stage_bytes;
 };
 
-template <int KP>
+// ---- cluster helpers (CTA pair, cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// Remote arrive with the default (release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) does: what the
+// barriers of this kernel order across the pair is asynchronous-proxy traffic (bulk copies into shared memory, tensor-core
+// reads of it, tensor-memory reads) that has already completed when the arrive is issued, so no cluster-scope
+// fence is needed -- .release.cluster / .acquire.cluster compile to MEMBAR.ALL.GPU + CCTL.IVALL per pipeline stage
+// and made the pair kernel 30% SLOWER than the single-CTA one.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        umma_tf32(d_tmem, da, db, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// arrive on the barrier (same offset in every CTA of the group) once all MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+    if constexpr (CG == 1) {
+        umma_commit(bar);
+    } else {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                smem_u32(bar)),
+            "h"((uint16_t)3)
+            : "memory");
+    }
+}
+
+// CG = 1: one CTA per SM, UMMA M = 128.
+// CG = 2: CTA pair (cluster of 2, cta_group::2), UMMA M = 256: the pair works on two adjacent voxel tiles against the
+//   same coefficient stream; each CTA stages its own X block and HALF of the coefficient block (the tensor cores
+//   of the pair share the halves), which halves the shared-memory and L2 traffic of the larger operand.
+//   Rank 0 issues the MMAs; rank 1's warp 1 relays "my stage has landed" to rank 0; MMA completion is multicast
+//   to the barriers of both CTAs; both epilogues report "accumulator drained" to rank 0.
+template <int KP, int CG>
 __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const TfArgs a) {
     constexpr int P = KP * 16 / (KP % 16 == 0 ? 16 : (KP % 8 == 0 ? 8 : (KP % 4 == 0 ? 4 : (KP % 2 == 0 ? 2 : 1))));
     constexpr int NCH = P / 16;   // 16-column chunks per period
@@ -202,23 +286,33 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.nstage * a.stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + 8;
-    uint64_t* tfull = bars + 16;
-    uint64_t* tempty = bars + 18;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* pfull = bars + 16;          // CG == 2, rank 0: the peer's stage has landed
+    uint64_t* tfull = bars + 24;
+    uint64_t* tempty = bars + 26;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const long long u_first = blockIdx.x / CG, u_step = gridDim.x / CG;
+    const uint32_t bhalf = a.b_plane / CG;              // bytes of one coefficient plane staged by this CTA
+    const uint32_t cta_stage_bytes = TF_A_STAGE + 2u * bhalf;
 
     if (tid == 0) {
-        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(pfull + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4 * CG); }
         mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
 
@@ -226,8 +320,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         // ===================== producer: stream the operand images into the ring =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (long long u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-                const long long vt = u % a.nvt;
+            for (long long u = u_first; u < a.nunits; u += u_step) {
+                const long long vt = (u % a.nvt) * CG + rank;
                 const int split = (int)(u / a.nvt);
                 const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
                 const char* asrc = reinterpret_cast<const char*>(a.aimg) + (size_t)vt * a.nkb * TF_A_STAGE;
@@ -236,51 +330,66 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     for (int kb = 0; kb < a.nkb; ++kb) {
                         mbar_wait(empty + stage, phase ^ 1u);
                         unsigned char* dst = ring + (size_t)stage * a.stage_bytes;
-                        mbar_expect_tx(full + stage, a.stage_bytes);
+                        mbar_expect_tx(full + stage, cta_stage_bytes);
                         bulk_g2s(dst, asrc + (size_t)kb * TF_A_STAGE, TF_A_STAGE, full + stage);
-                        const char* bs = bsrc + (size_t)kb * (2u * a.b_plane);
-                        const uint32_t bbytes = 2u * a.b_plane;
-#pragma unroll 1
-                        for (uint32_t off = 0; off < bbytes; off += 16384u)
-                            bulk_g2s(dst + TF_A_STAGE + off, bs + off, min(16384u, bbytes - off), full + stage);
+                        const char* bs = bsrc + (size_t)kb * (2u * a.b_plane) + rank * bhalf;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)      // hi plane, lo plane (this CTA's rows of each)
+                            bulk_g2s(dst + TF_A_STAGE + h * bhalf, bs + (size_t)h * a.b_plane, bhalf, full + stage);
                         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.ntile >> 3) << 17) | ((128u >> 4) << 24);
+        if (lane == 0 && rank == 0) {
+            // ===================== MMA issuer (single thread of the leader CTA) =====================
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.ntile >> 3) << 17) |
+                                   ((uint32_t)((128 * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
             const uint32_t ring_s = smem_u32(ring);
-            for (long long u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+            for (long long u = u_first; u < a.nunits; u += u_step) {
                 const int split = (int)(u / a.nvt);
                 const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
                 for (int ct = ct0; ct < ct1; ++ct) {
-                    mbar_wait(tempty + as, aphase ^ 1u);
+                    if constexpr (CG == 2) mbar_wait_cluster(tempty + as, aphase ^ 1u);
+                    else mbar_wait(tempty + as, aphase ^ 1u);
                     tc_fence_after();
                     const uint32_t d = tbase + (uint32_t)as * 256u;
                     for (int kb = 0; kb < a.nkb; ++kb) {
                         mbar_wait(full + stage, phase);
+                        if constexpr (CG == 2) mbar_wait_cluster(pfull + stage, phase);
                         tc_fence_after();
                         const uint32_t sa = ring_s + (uint32_t)stage * a.stage_bytes;
                         const uint32_t sb = sa + TF_A_STAGE;
                         const int nks = (kb == a.nkb - 1) ? a.nks_last : 2;
                         for (int ks = 0; ks < nks; ++ks) {
                             const uint64_t ah = umma_desc_sw64(sa + ks * 32u), al = umma_desc_sw64(sa + TF_A_PLANE + ks * 32u);
-                            const uint64_t bh = umma_desc_sw64(sb + ks * 32u), bl = umma_desc_sw64(sb + a.b_plane + ks * 32u);
+                            const uint64_t bh = umma_desc_sw64(sb + ks * 32u), bl = umma_desc_sw64(sb + bhalf + ks * 32u);
                             // small cross terms first, leading term last
-                            umma_tf32(d, ah, bl, idesc, (kb | ks) ? 1u : 0u);
-                            umma_tf32(d, al, bh, idesc, 1u);
-                            umma_tf32(d, ah, bh, idesc, 1u);
+                            umma_tf32_cg<CG>(d, ah, bl, idesc, (kb | ks) ? 1u : 0u);
+                            umma_tf32_cg<CG>(d, al, bh, idesc, 1u);
+                            umma_tf32_cg<CG>(d, ah, bh, idesc, 1u);
                         }
-                        umma_commit(empty + stage);          // frees the smem slot once these MMAs have read it
+                        umma_commit_cg<CG>(empty + stage);       // frees the smem slot (in both CTAs) once read
                         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
                     }
-                    umma_commit(tfull + as);                 // accumulator complete -> epilogue
+                    umma_commit_cg<CG>(tfull + as);              // accumulator complete -> epilogue(s)
                     if (++as == 2) { as = 0; aphase ^= 1u; }
                 }
+            }
+        } else if (CG == 2 && lane == 0) {
+            // ===================== relay (rank 1): tell the leader that my stage has landed =====================
+            int stage = 0; uint32_t phase = 0;
+            for (long long u = u_first; u < a.nunits; u += u_step) {
+                const int split = (int)(u / a.nvt);
+                const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
+                for (int ct = ct0; ct < ct1; ++ct)
+                    for (int kb = 0; kb < a.nkb; ++kb) {
+                        mbar_wait(full + stage, phase);
+                        mbar_arrive_cluster(mapa_u32(smem_u32(pfull + stage), 0));
+                        if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
+                    }
             }
         }
     } else {
@@ -288,8 +397,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
         int as = 0; uint32_t aphase = 0;
-        for (long long u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-            const long long vt = u % a.nvt;
+        const uint32_t tempty0 = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : smem_u32(tempty);
+        for (long long u = u_first; u < a.nunits; u += u_step) {
+            const long long vt = (u % a.nvt) * CG + rank;
             const int split = (int)(u / a.nvt);
             const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
             const long long v = vt * TF_MV + row;
@@ -342,7 +452,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty + as);
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + (uint32_t)as * 8u);
+                    else mbar_arrive(tempty + as);
+                }
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
             if (v < a.p) {
@@ -354,11 +467,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
             }
         }
     }
+    __syncwarp();            // re-converge the warps whose lane 0 ran a role loop before the aligned barriers
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
     }
 }
 
@@ -371,14 +486,28 @@ __global__ void moments_reduce_tf32_kernel(const double* __restrict__ part1, con
     sum[i] = x; sumsq[i] = y;
 }
 
-template <int KP>
-static int launch_tf32(const TfPlan& t, const TfArgs& a, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_tf32_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int KP, int CG>
+static int launch_tf32_cg(const TfPlan& t, const TfArgs& a, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_tf32_kernel<KP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)t.smem_bytes));
-    const long long grid = a.nunits < num_sms() ? a.nunits : num_sms();
-    boot_moments_tf32_kernel<KP><<<(unsigned)grid, TF_THREADS, t.smem_bytes, st>>>(a);
+    const long long groups = a.nunits < num_sms() / CG ? a.nunits : num_sms() / CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * CG));
+    cfg.blockDim = dim3(TF_THREADS);
+    cfg.dynamicSmemBytes = t.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    PLSB_CUDA(cudaLaunchKernelEx(&cfg, boot_moments_tf32_kernel<KP, CG>, a));
     PLSB_LAUNCH_CHECK("boot_moments_tf32_kernel");
     return PLSB200_OK;
+}
+template <int KP>
+static int launch_tf32(const TfPlan& t, const TfArgs& a, cudaStream_t st) {
+    return t.cg == 2 ? launch_tf32_cg<KP, 2>(t, a, st) : launch_tf32_cg<KP, 1>(t, a, st);
 }
 
 }  // namespace plsb
@@ -387,7 +516,7 @@ using namespace plsb;
 
 extern "C" size_t plsb200_tf32_ximage_bytes(int N, int64_t p) {
     if (N < 1 || p < 1) return 0;
-    return (size_t)cdiv(p, TF_MV) * (size_t)cdiv(N, TF_KB) * TF_A_STAGE;
+    return (size_t)(2 * cdiv(cdiv(p, TF_MV), 2)) * (size_t)cdiv(N, TF_KB) * TF_A_STAGE;   // tile count padded to even
 }
 
 extern "C" int plsb200_tf32_split_x(const double* X, int N, int64_t p, int64_t ldx, void* ximage, void* stream) {
@@ -395,7 +524,7 @@ extern "C" int plsb200_tf32_split_x(const double* X, int N, int64_t p, int64_t l
     PLSB_CHECK_ARG(N > 0 && p > 0 && ldx >= p, "tf32_split_x: bad shape");
     const int nkb = (int)cdiv(N, TF_KB);
     PLSB_CHECK_ARG(nkb <= 65535, "tf32_split_x: N too large");
-    dim3 grid((unsigned)cdiv(p, TF_MV), (unsigned)nkb);
+    dim3 grid((unsigned)(2 * cdiv(cdiv(p, TF_MV), 2)), (unsigned)nkb);      // padding tile is written as zeros
     split_x_tf32_kernel<<<grid, TF_MV, 0, (cudaStream_t)stream>>>(X, N, p, ldx, nkb, (float*)ximage);
     PLSB_LAUNCH_CHECK("split_x_tf32_kernel");
     return PLSB200_OK;
@@ -416,13 +545,13 @@ extern "C" int plsb200_boot_coef_pack_tf32(const double* E, int N, int K, const 
         return PLSB200_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ids_bytes = (size_t)((N + 1) / 2) * sizeof(double);
-    const int stage_e = (size_t)N * K * sizeof(double) + ids_bytes <= 48 * 1024;
-    const size_t smem = ids_bytes + (stage_e ? (size_t)N * K * sizeof(double) : 0);
+    const size_t fixed = (size_t)2 * CP_KB * K * TF_KB * sizeof(float) + (size_t)((N + 1) & ~1) * sizeof(int);
+    const int stage_e = (size_t)N * K * sizeof(double) + fixed <= 96 * 1024;
+    const size_t smem = fixed + (stage_e ? (size_t)N * K * sizeof(double) : 0);
     PLSB_CHECK_ARG(smem <= 200 * 1024, "boot_coef_pack_tf32: N=%d too large", N);
     PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)t.nct * t.nkb * 2 * t.b_plane, st));
     PLSB_CUDA(cudaFuncSetAttribute(coef_pack_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coef_pack_tf32_kernel<<<R, 256, smem, st>>>(E, N, K, idx, t.Kp, t.nres, t.ntile, t.nkb, stage_e, (float*)coef);
+    coef_pack_tf32_kernel<<<R, CP_ROWS, smem, st>>>(E, N, K, idx, t.Kp, t.nres, t.ntile, t.nkb, stage_e, (float*)coef);
     PLSB_LAUNCH_CHECK("coef_pack_tf32_kernel");
     return PLSB200_OK;
 }

@@ -142,39 +142,39 @@ __global__ void uhat_kernel(const double* __restrict__ XL, long long xl_stride, 
 }
 
 // population std over axis 0 of A[R][M], two-pass like numpy (mean, then mean of squared deviations).
-// One warp per column strip of 32 columns x all rows would serialise R loads; instead a CTA owns 32
-// columns, its 8 warps stride over the rows (coalesced 256-B row segments) and the per-warp partials
-// are combined in a fixed order through shared memory (deterministic).
-__global__ void __launch_bounds__(256) colstd_kernel(const double* __restrict__ A, int R, long long M,
-                                                    double* __restrict__ out) {
-    __shared__ double part[8][33];
-    __shared__ double mean[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long m = (long long)blockIdx.x * 32 + lane;
+// A CTA owns CS_COLS columns; its 1024 threads form CS_COLS x 128 (column, row-lane) pairs that stride over the
+// rows, and the row-lane partials are combined by a fixed-order tree in shared memory (deterministic).
+constexpr int CS_COLS = 8;
+constexpr int CS_ROWS = 128;
+__device__ __forceinline__ double colstd_block_sum(double v, double* red, int col, int rl) {
+    red[rl * CS_COLS + col] = v;
+    __syncthreads();
+    for (int h = CS_ROWS / 2; h > 0; h >>= 1) {
+        if (rl < h) red[rl * CS_COLS + col] += red[(rl + h) * CS_COLS + col];
+        __syncthreads();
+    }
+    const double t = red[col];
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(CS_COLS * CS_ROWS) colstd_kernel(const double* __restrict__ A, int R, long long M,
+                                                                 double* __restrict__ out) {
+    __shared__ double red[CS_ROWS * CS_COLS];
+    const int col = threadIdx.x % CS_COLS, rl = threadIdx.x / CS_COLS;
+    const long long m = (long long)blockIdx.x * CS_COLS + col;
     const bool ok = m < M;
     double s = 0.0;
-    for (int r = warp; r < R; r += 8) s += ok ? A[(size_t)r * M + m] : 0.0;
-    part[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += part[w][lane];
-        mean[lane] = t / R;
-    }
-    __syncthreads();
-    const double mu = mean[lane];
+#pragma unroll 4
+    for (int r = rl; r < R; r += CS_ROWS) s += ok ? __ldg(A + (size_t)r * M + m) : 0.0;
+    const double mu = colstd_block_sum(s, red, col, rl) / R;
     double q = 0.0;
-    for (int r = warp; r < R; r += 8) {
-        const double d = ok ? A[(size_t)r * M + m] - mu : 0.0;
+#pragma unroll 4
+    for (int r = rl; r < R; r += CS_ROWS) {
+        const double d = ok ? __ldg(A + (size_t)r * M + m) - mu : 0.0;
         q = fma(d, d, q);
     }
-    part[warp][lane] = q;
-    __syncthreads();
-    if (warp == 0 && ok) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += part[w][lane];
-        out[m] = sqrt(t / R);
-    }
+    const double t = colstd_block_sum(q, red, col, rl);
+    if (rl == 0 && ok) out[m] = sqrt(t / R);
 }
 
 template <int KT>
@@ -273,7 +273,7 @@ extern "C" int plsb200_uhat_f64(const double* XL, int64_t xl_stride, int N, int 
 extern "C" int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* stream) {
     PLSB_CHECK_ARG(A && out, "colstd_f64: null pointer");
     PLSB_CHECK_ARG(R > 0 && M > 0, "colstd_f64: bad shape");
-    colstd_kernel<<<(int)cdiv(M, 32), 256, 0, (cudaStream_t)stream>>>(A, R, M, out);
+    colstd_kernel<<<(unsigned)cdiv(M, CS_COLS), CS_COLS * CS_ROWS, 0, (cudaStream_t)stream>>>(A, R, M, out);
     PLSB_LAUNCH_CHECK("colstd_kernel");
     return PLSB200_OK;
 }

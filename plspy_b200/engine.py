@@ -67,9 +67,10 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def to_host(self, *tensors):
-        """Device -> host through pinned staging buffers (torch's caching host allocator), one
-        synchronisation for the whole batch; returns numpy arrays (None passes through)."""
+    def to_host_async(self, *tensors):
+        """Enqueue device -> host copies into pinned staging buffers (torch's caching host allocator) and return
+        a function that waits for them (one event synchronisation) and hands back numpy arrays; None passes
+        through.  Lets the caller keep enqueuing GPU work before it blocks."""
         staged = []
         for t in tensors:
             if t is None:
@@ -78,9 +79,18 @@ class Engine:
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t, non_blocking=True)
             staged.append(h)
-        torch.cuda.current_stream(self.device).synchronize()
-        out = [None if h is None else h.numpy() for h in staged]
-        return out[0] if len(out) == 1 else out
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+
+        def wait():
+            done.synchronize()
+            out = [None if h is None else h.numpy() for h in staged]
+            return out[0] if len(out) == 1 else out
+        return wait
+
+    def to_host(self, *tensors):
+        """Device -> host through pinned staging buffers, one synchronisation for the whole batch."""
+        return self.to_host_async(*tensors)()
 
     def _empty(self, *shape, dtype=F64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
