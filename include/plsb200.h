@@ -225,6 +225,25 @@ int plsb200_split_svd_f64(const double* S11, const double* S12, const double* S2
                           double* s_train, double* s_test, double* u_repro, double* v_repro, double* s2,
                           void* stream);
 
+/* ---- host-side resampling index generator (no GPU work) -------------------------------------------------
+ * Continues numpy's legacy global MT19937 stream -- `key` = the 624 state words, `*pos` = the position, both as
+ * returned by np.random.get_state() and updated in place -- with numpy's own algorithms (masked-rejection
+ * random_interval, RandomState.shuffle, RandomState.choice), so the index matrices are bit-identical to what
+ * the reference draws through resample_without_replacement / resample_with_replacement
+ * (plspy/core/resample.py:44-79, 125-160; call order SURVEY.md App. B) at ~100x the speed of the numpy calls.
+ * cond_order: G x C int32 (subjects per group and condition; must be constant within a group, else
+ * PLSB200_EUNSUPPORTED and the caller falls back to numpy).
+ *  task_permutations: count x N task-method permutation index vectors; beh_rows > 0 adds, after every draw, one
+ *    np.random.permutation(beh_rows) for the multiblock behaviour block (bootstrap_permutation.py:342-347).
+ *  bootstrap_draws: count x N bootstrap index vectors; cond_order2 != NULL adds the independent behaviour-block
+ *    draw of the multiblock methods (bootstrap_permutation.py:545-554).
+ *  row_permutations: count x n, np.random.permutation(n) each (behaviour PLS, :337-340).                    */
+int plsb200_host_task_permutations(uint32_t* key, int32_t* pos, const int32_t* cond_order, int G, int C,
+                                   int beh_rows, int count, int32_t* out_task, int32_t* out_beh);
+int plsb200_host_bootstrap_draws(uint32_t* key, int32_t* pos, const int32_t* cond_order, int G, int C,
+                                 const int32_t* cond_order2, int C2, int count, int32_t* out, int32_t* out2);
+int plsb200_host_row_permutations(uint32_t* key, int32_t* pos, int n, int count, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

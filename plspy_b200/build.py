@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libplsb200.so")
-SOURCES = ["abi.cu", "gram.cu", "nspace.cu", "boot.cu", "boot_rs.cu", "boot_tf32.cu", "split.cu", "rb.cu"]
+SOURCES = ["abi.cu", "gram.cu", "nspace.cu", "boot.cu", "boot_rs.cu", "boot_tf32.cu", "split.cu", "rb.cu", "host_rng.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        o = os.path.join(CSRC, os.path.splitext(s)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")

@@ -2,9 +2,55 @@
 RNG (plspy/core/resample.py:9-165; call order SURVEY.md App. B), so that `np.random.seed(k)` followed
 by PLS(...) draws the same resamples here as in plspy.  The gathers themselves happen on the GPU.
 """
+import ctypes
+
 import numpy as np
 
 from . import class_functions
+
+# native generator (csrc/host_rng.cpp) continuing numpy's global MT19937 stream; set to False to force the
+# numpy path (tests compare the two)
+USE_NATIVE_RNG = True
+
+
+def _native(name, co, count, *tail):
+    """Run one of the plsb200_host_* generators on the global numpy stream.  `tail` are the remaining C
+    arguments; returns True on success (state advanced), False if the design is not supported natively."""
+    from ._lib import lib, PlsB200Error
+    st = np.random.get_state(legacy=True)
+    key = np.array(st[1], dtype=np.uint32, copy=True)
+    pos = ctypes.c_int32(int(st[2]))
+    fn = getattr(lib, name)
+    if co is None:
+        rc = fn(key.ctypes.data, ctypes.addressof(pos), *tail)
+    else:
+        co = np.ascontiguousarray(co, dtype=np.int32)
+        rc = fn(key.ctypes.data, ctypes.addressof(pos), co.ctypes.data, co.shape[0], co.shape[1], *tail)
+    if rc == -4:      # PLSB200_EUNSUPPORTED: ragged design
+        return False
+    if rc != 0:
+        raise PlsB200Error(f"{name} failed (code {rc})")
+    np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+    return True
+
+
+def _draws_ok(Y, idx, cond_order, chunk=512):
+    """Vectorised acceptance test of the re-draw loops for a whole batch of index vectors: True only when every
+    draw is clearly acceptable (no group with a (near-)constant resampled behaviour column); anything doubtful
+    returns False and the caller replays the reference's sequential loop, whose `std == 0` test is then exact."""
+    import warnings
+    co = np.asarray(cond_order)
+    sizes = co.sum(axis=1)
+    starts = np.concatenate(([0], np.cumsum(sizes)))
+    tiny = 1e-10 * (np.abs(Y).max() + 1e-300)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i0 in range(0, idx.shape[0], chunk):
+            Yn = Y[idx[i0:i0 + chunk]]                       # (chunk, N, nb)
+            for g in range(co.shape[0]):
+                if (Yn[:, starts[g]:starts[g + 1], :].std(axis=1) <= tiny).any():
+                    return False
+    return True
 
 
 def _subject_grids(cond_order):
@@ -53,6 +99,10 @@ def permutation_indices(pls_alg, nperm, cond_order, Y=None, bscan=None, Ybscan=N
     """Index vectors of all permutations (bootstrap_permutation.py:323-355).
     Returns (task (P x N) int32 or None, behaviour (P x Nb) int32 or None)."""
     co = np.asarray(cond_order)
+    if USE_NATIVE_RNG and nperm > 0:
+        out = _native_permutations(pls_alg, nperm, co, Y, Ybscan)
+        if out is not None:
+            return out
     grid = np.concatenate(_subject_grids(co))
     task, beh = [], []
     for _ in range(nperm):
@@ -78,10 +128,63 @@ def permutation_indices(pls_alg, nperm, cond_order, Y=None, bscan=None, Ybscan=N
     return as32(task), as32(beh)
 
 
+def _native_permutations(pls_alg, nperm, co, Y, Ybscan):
+    """All permutations in one native call.  The re-draw loops of the behaviour methods accept the first attempt
+    unless a group's resampled behaviour column is constant; the batch is validated afterwards and, if any draw
+    would have been rejected, the global stream is rewound and None returned (the caller then replays the
+    reference's sequential loop)."""
+    N = int(co.sum())
+    saved = np.random.get_state(legacy=True)
+    task = beh = None
+    if pls_alg in ("mct", "cst"):
+        task = np.empty((nperm, N), dtype=np.int32)
+        ok = _native("plsb200_host_task_permutations", co, nperm, 0, nperm, task.ctypes.data, None)
+    elif pls_alg in ("rb", "csb"):
+        beh = np.empty((nperm, Y.shape[0]), dtype=np.int32)
+        ok = _native("plsb200_host_row_permutations", None, nperm, Y.shape[0], nperm, beh.ctypes.data)
+        ok = ok and _draws_ok(Y, beh, co)
+    else:
+        Nb = Ybscan.shape[0]
+        task = np.empty((nperm, N), dtype=np.int32); beh = np.empty((nperm, Nb), dtype=np.int32)
+        ok = _native("plsb200_host_task_permutations", co, nperm, Nb, nperm, task.ctypes.data, beh.ctypes.data)
+        # the reference applies the full-design group sizes to the bscan-reduced Y (App. C quirk 10): rows beyond
+        # Nb do not exist, numpy slicing clips them
+        ok = ok and _draws_ok(Ybscan, beh, co)
+    if not ok:
+        np.random.set_state(saved)
+        return None
+    return task, beh
+
+
+def _native_bootstraps(pls_alg, nboot, co, Y, bscan, Ybscan):
+    N = int(co.sum())
+    saved = np.random.get_state(legacy=True)
+    main = np.empty((nboot, N), dtype=np.int32)
+    beh = None
+    if pls_alg in ("mb", "cmb"):
+        co2 = np.ascontiguousarray(co[:, bscan], dtype=np.int32)
+        beh = np.empty((nboot, int(co2.sum())), dtype=np.int32)
+        ok = _native("plsb200_host_bootstrap_draws", co, nboot, co2.ctypes.data, co2.shape[1], nboot,
+                     main.ctypes.data, beh.ctypes.data)
+        ok = ok and _draws_ok(Ybscan, beh, co)
+    else:
+        ok = _native("plsb200_host_bootstrap_draws", co, nboot, None, 0, nboot, main.ctypes.data, None)
+        if Y is not None:
+            ok = ok and _draws_ok(Y, main, co)
+    if not ok:
+        np.random.set_state(saved)
+        return None
+    return main, beh
+
+
 def bootstrap_indices(pls_alg, nboot, cond_order, Y=None, bscan=None, Ybscan=None):
     """Index vectors of all bootstraps (bootstrap_permutation.py:537-572).
     Returns (main (B x N) int32, behaviour-block (B x Nb) int32 or None)."""
     co = np.asarray(cond_order)
+    if USE_NATIVE_RNG and nboot > 0:
+        out = _native_bootstraps(pls_alg, nboot, co, Y, bscan, Ybscan)
+        if out is not None:
+            return out
     grids = _subject_grids(co)
     grids_b = _subject_grids(co[:, bscan]) if pls_alg in ("mb", "cmb") else None
     main, beh = [], []

@@ -169,3 +169,59 @@ def test_product_does_not_import_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(root, f)).read()
             assert "import oracle" not in src and "from oracle" not in src, f
+
+
+# ---- native index generator (csrc/host_rng.cpp) vs numpy's own legacy RNG calls ------------------------------
+@pytest.mark.parametrize("alg,co,extra", [
+    ("mct", [[25] * 4] * 3, {}),
+    ("cst", [[7] * 3, [9] * 3], {}),
+    ("mct", [[1] * 2, [5] * 2], {}),                 # a one-subject group: choice(1, 1) draws nothing
+    ("mct", [[4], [6]], {}),                         # single condition
+    ("rb", [[20] * 3] * 2, {"Y": (120, 4)}),
+    ("csb", [[5] * 2] * 2, {"Y": (20, 2)}),
+    ("mb", [[6] * 4, [8] * 4], {"bscan": [1, 2], "Ybscan": (28, 3)}),
+    ("cmb", [[6] * 3] * 2, {"bscan": [0, 2], "Ybscan": (24, 2)}),
+])
+def test_native_index_generator_is_bit_identical_to_numpy(alg, co, extra):
+    """Same index matrices AND same stream position afterwards, from an arbitrary position of the global stream
+    (state regeneration boundaries included: 300 draws of this size consume many 624-word blocks)."""
+    from plspy_b200 import resample
+    co = np.array(co)
+    rs = np.random.RandomState(0)
+    kw = {k: (rs.standard_normal(v) if isinstance(v, tuple) else v) for k, v in extra.items()}
+    res = []
+    for native in (False, True):
+        resample.USE_NATIVE_RNG = native
+        try:
+            np.random.seed(4321)
+            np.random.random(11)
+            a = resample.permutation_indices(alg, 300, co, **{k: v for k, v in kw.items() if k != "bscan" or True})
+            b = resample.bootstrap_indices(alg, 300, co, **kw)
+            res.append((a, b, np.random.random(4)))
+        finally:
+            resample.USE_NATIVE_RNG = True
+    for x, y in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
+        assert (x is None and y is None) or (x.dtype == y.dtype and np.array_equal(x, y))
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+
+
+def test_native_index_generator_falls_back_on_rejected_draws():
+    """A behaviour column that is constant inside a group makes the reference's re-draw loop reject draws: the
+    native batch must notice, rewind the stream and leave the work to the sequential path (which raises)."""
+    from plspy_b200 import resample
+    co = np.array([[4] * 2] * 2)
+    Y = np.random.RandomState(1).standard_normal((16, 2))
+    Y[:, 0] = 3.0
+    np.random.seed(5)
+    with pytest.raises(Exception, match="behaviour data"):
+        resample.permutation_indices("rb", 5, co, Y=Y)
+
+
+def test_native_index_generator_ragged_design_uses_numpy():
+    from plspy_b200 import resample
+    from plspy_b200._lib import lib
+    co = np.ascontiguousarray([[3, 4]], dtype=np.int32)
+    key = np.zeros(624, np.uint32); import ctypes
+    pos = ctypes.c_int32(624); out = np.zeros((1, 7), np.int32)
+    assert lib.plsb200_host_task_permutations(key.ctypes.data, ctypes.addressof(pos), co.ctypes.data, 1, 2, 0, 1,
+                                              out.ctypes.data, None) == -4
