@@ -52,7 +52,9 @@ static bool tf_plan(int N, int K, int R, int64_t p, TfPlan& t) {
     t.nct = (int)cdiv(R, t.nres);
     t.b_plane = (uint32_t)t.ntile * TF_KB * 4;
     const char* env = getenv("PLSB200_TF32_CTA_GROUP");
-    t.cg = (env && env[0] == '1') ? 1 : 2;
+    // default: single CTA (measured 26.3-26.7 ms on the bench workload vs 26.9-27.8 ms for the pair, which moves a
+    // third less data through L2 / shared memory but is held back by the tensor pipe all the same)
+    t.cg = (env && env[0] == '2') ? 2 : 1;
     t.stage_bytes = TF_A_STAGE + 2 * t.b_plane / t.cg;
     int ns = (int)((227 * 1024 - 2048) / t.stage_bytes);
     if (ns > 8) ns = 8;
@@ -216,6 +218,7 @@ struct TfArgs {
     long long p, nvt, nunits;
     int K, R, nkb, nks_last, ntile, nres, nct, ct_per_split, nstage;
     uint32_t b_plane, stage_bytes;
+    long long* trace;      // optional (PLSB200_TF32_TRACE=1): per-CTA cycle counters of the role loops, 8 per CTA
 };
 
 // ---- cluster helpers (CTA pair, cta_group::2)
@@ -320,6 +323,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         // ===================== producer: stream the operand images into the ring =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             for (long long u = u_first; u < a.nunits; u += u_step) {
                 const long long vt = (u % a.nvt) * CG + rank;
                 const int split = (int)(u / a.nvt);
@@ -328,7 +333,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 for (int ct = ct0; ct < ct1; ++ct) {
                     const char* bsrc = reinterpret_cast<const char*>(a.bimg) + (size_t)ct * a.nkb * (2u * a.b_plane);
                     for (int kb = 0; kb < a.nkb; ++kb) {
+                        const long long tw = clock64();
                         mbar_wait(empty + stage, phase ^ 1u);
+                        w_empty += clock64() - tw;
                         unsigned char* dst = ring + (size_t)stage * a.stage_bytes;
                         mbar_expect_tx(full + stage, cta_stage_bytes);
                         bulk_g2s(dst, asrc + (size_t)kb * TF_A_STAGE, TF_A_STAGE, full + stage);
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     }
                 }
             }
+            if (a.trace) { a.trace[blockIdx.x * 8 + 4] = clock64() - t_begin; a.trace[blockIdx.x * 8 + 5] = w_empty; }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
@@ -348,17 +356,25 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                                    ((uint32_t)((128 * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
             const uint32_t ring_s = smem_u32(ring);
+            long long w_full = 0, w_pfull = 0, w_tempty = 0;
+            const long long t_begin = clock64();
             for (long long u = u_first; u < a.nunits; u += u_step) {
                 const int split = (int)(u / a.nvt);
                 const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
                 for (int ct = ct0; ct < ct1; ++ct) {
+                    long long tw = clock64();
                     if constexpr (CG == 2) mbar_wait_cluster(tempty + as, aphase ^ 1u);
                     else mbar_wait(tempty + as, aphase ^ 1u);
+                    w_tempty += clock64() - tw;
                     tc_fence_after();
                     const uint32_t d = tbase + (uint32_t)as * 256u;
                     for (int kb = 0; kb < a.nkb; ++kb) {
+                        tw = clock64();
                         mbar_wait(full + stage, phase);
+                        const long long tw2 = clock64();
                         if constexpr (CG == 2) mbar_wait_cluster(pfull + stage, phase);
+                        w_full += tw2 - tw;
+                        w_pfull += clock64() - tw2;
                         tc_fence_after();
                         const uint32_t sa = ring_s + (uint32_t)stage * a.stage_bytes;
                         const uint32_t sb = sa + TF_A_STAGE;
@@ -377,6 +393,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     umma_commit_cg<CG>(tfull + as);              // accumulator complete -> epilogue(s)
                     if (++as == 2) { as = 0; aphase ^= 1u; }
                 }
+            }
+            if (a.trace) {
+                long long* t = a.trace + blockIdx.x * 8;
+                t[0] = clock64() - t_begin; t[1] = w_full; t[2] = w_pfull; t[3] = w_tempty;
             }
         } else if (CG == 2 && lane == 0) {
             // ===================== relay (rank 1): tell the leader that my stage has landed =====================
@@ -398,6 +418,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         const int row = quarter * 32 + lane;
         int as = 0; uint32_t aphase = 0;
         const uint32_t tempty0 = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : smem_u32(tempty);
+        long long w_tfull = 0;
+        const long long t_begin = clock64();
         for (long long u = u_first; u < a.nunits; u += u_step) {
             const long long vt = (u % a.nvt) * CG + rank;
             const int split = (int)(u / a.nvt);
@@ -411,7 +433,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 s1[k] = 0.0; s2[k] = 0.0;
             }
             for (int ct = ct0; ct < ct1; ++ct) {
+                const long long tw = clock64();
                 mbar_wait(tfull + as, aphase);
+                w_tfull += clock64() - tw;
                 tc_fence_after();
                 const uint32_t t0 = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
                 const int nvalid = min(a.nres, a.R - ct * a.nres) * KP;     // valid columns of this tile
@@ -465,6 +489,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 for (int k = 0; k < KP; ++k)
                     if (k < a.K) { o1[k] = s1[k]; o2[k] = s2[k]; }
             }
+        }
+        if (a.trace && warp == 2 && lane == 0) {
+            a.trace[blockIdx.x * 8 + 6] = clock64() - t_begin; a.trace[blockIdx.x * 8 + 7] = w_tfull;
         }
     }
     __syncwarp();            // re-converge the warps whose lane 0 ran a role loop before the aligned barriers
@@ -588,6 +615,12 @@ extern "C" int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, c
     a.p = p; a.nvt = t.nvt; a.nunits = t.nvt * t.nsplit;
     a.K = K; a.R = R; a.nkb = t.nkb; a.nks_last = t.nks_last; a.ntile = t.ntile; a.nres = t.nres; a.nct = t.nct;
     a.ct_per_split = t.ct_per_split; a.nstage = t.nstage; a.b_plane = t.b_plane; a.stage_bytes = t.stage_bytes;
+    a.trace = nullptr;
+    const bool trace = getenv("PLSB200_TF32_TRACE") != nullptr;
+    if (trace) {
+        PLSB_CUDA(cudaMalloc(&a.trace, 148 * 8 * sizeof(long long)));
+        PLSB_CUDA(cudaMemsetAsync(a.trace, 0, 148 * 8 * sizeof(long long), st));
+    }
     int rc;
     switch (t.Kp) {
 #define PLSB_TF(kp) case kp: rc = launch_tf32<kp>(t, a, st); break;
@@ -599,6 +632,25 @@ extern "C" int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, c
             return PLSB200_EUNSUPPORTED;
     }
     if (rc != PLSB200_OK) return rc;
+    if (trace) {      // development aid: synchronous dump of the role-loop cycle counters (mean over CTAs)
+        long long h[148 * 8];
+        PLSB_CUDA(cudaStreamSynchronize(st));
+        PLSB_CUDA(cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(a.trace);
+        double m[8] = {0};
+        int nmma = 0, nall = 0;
+        for (int c = 0; c < 148; ++c) {
+            if (h[c * 8 + 4] == 0) continue;
+            ++nall;
+            for (int j = 4; j < 8; ++j) m[j] += (double)h[c * 8 + j];
+            if (h[c * 8] != 0) { ++nmma; for (int j = 0; j < 4; ++j) m[j] += (double)h[c * 8 + j]; }
+        }
+        fprintf(stderr,
+                "[plsb200 tf32 trace] cg=%d nstage=%d | MMA thread: total %.0f cyc, wait full %.1f%%, wait peer-full %.1f%%, "
+                "wait tmem-empty %.1f%% | producer: total %.0f, wait empty %.1f%% | epilogue: total %.0f, wait tmem-full %.1f%%\n",
+                t.cg, t.nstage, m[0] / nmma, 100 * m[1] / m[0], 100 * m[2] / m[0], 100 * m[3] / m[0], m[4] / nall,
+                100 * m[5] / m[4], m[6] / nall, 100 * m[7] / m[6]);
+    }
     if (t.nsplit > 1) {
         const long long n = (long long)p * K;
         moments_reduce_tf32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(o1, o2, t.nsplit, n, sum, sumsq);

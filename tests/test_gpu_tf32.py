@@ -59,6 +59,26 @@ def test_boot_moments_tf32(N, p, K, R):
     np.testing.assert_allclose(br.cpu().numpy(), pivot / VS.std(0), rtol=2e-5)
 
 
+@pytest.mark.parametrize("N,p,K,R", [(300, 777, 12, 45), (60, 1000, 6, 50), (77, 200, 16, 40), (1200, 300, 24, 12),
+                                     (36, 130, 3, 500)])
+def test_boot_moments_tf32_cta_pair(N, p, K, R, monkeypatch):
+    """the cta_group::2 variant (cluster of two CTAs, UMMA M = 256, odd tile counts zero-padded) gives the same
+    moments as the single-CTA kernel up to FP32 accumulation order"""
+    import torch
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(N, p, K, R, 7 + N + K, offset=0.25)
+    pivot = np.random.RandomState(3).standard_normal((p, K))
+    eng = Engine(X, precision="tf32x3")
+    monkeypatch.setenv("PLSB200_TF32_CTA_GROUP", "1")
+    a1, a2 = eng.boot_moments(E, idx, pivot)
+    monkeypatch.setenv("PLSB200_TF32_CTA_GROUP", "2")
+    b1, b2 = eng.boot_moments(E, idx, pivot)
+    torch.testing.assert_close(b1, a1, rtol=1e-5, atol=1e-6 * a1.abs().max().item())
+    torch.testing.assert_close(b2, a2, rtol=1e-5, atol=1e-6 * a2.abs().max().item())
+    VS = np.stack([X.T @ _scatter(E, idx[r]) for r in range(R)]) - pivot
+    np.testing.assert_allclose(b2.cpu().numpy(), (VS ** 2).sum(0), rtol=2e-5, atol=1e-5 * (VS ** 2).sum(0).max())
+
+
 def test_boot_moments_tf32_matches_fp64_large():
     """many voxel tiles and work units per CTA (persistent loop, accumulator-stage phases), deterministic"""
     import torch

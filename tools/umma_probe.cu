@@ -109,6 +109,86 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
 }
 
+// ---- issue-rate calibration: one thread issues `iters` x 6 kind::tf32 MMAs (128 x N x 8) on resident shared-memory
+// operands, all CTAs of the grid at once (power/clock as in a real kernel); cycles per MMA from clock64.
+template <int N>
+__global__ void __launch_bounds__(128) issue_rate(long long* cycles, int iters) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    float* sA = reinterpret_cast<float*>(sm);
+    float* sB = sA + 128 * 16;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + N) * 16; i += 128) sA[i] = 1.0f + (float)(i % 7) * 0.125f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t da0 = make_desc(smem_u32(sA), 1, 128), da1 = make_desc(smem_u32(sA) + 32, 1, 128);
+        const uint64_t db0 = make_desc(smem_u32(sB), 1, N), db1 = make_desc(smem_u32(sB) + 32, 1, N);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t d = tbase + (uint32_t)(it & 1) * 256u;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const uint64_t da = (j & 1) ? da1 : da0, db = (j & 1) ? db1 : db0;
+                asm volatile(
+                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+                    "l"(da), "l"(db), "r"(idesc), "r"(1u)
+                    : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar))
+                     : "memory");
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(ok)
+                : "r"(smem_u32(&bar)), "r"(0u)
+                : "memory");
+        }
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
+}
+
+template <int N>
+static void run_issue_rate(int grid) {
+    long long* d; CK(cudaMalloc(&d, grid * sizeof(long long)));
+    const size_t smem = (size_t)(128 + N) * 16 * 4 + 1024;
+    CK(cudaFuncSetAttribute(issue_rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int iters = 20000;
+    issue_rate<N><<<grid, 128, smem>>>(d, 1000);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    issue_rate<N><<<grid, 128, smem>>>(d, iters);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> h(grid); CK(cudaMemcpy(h.data(), d, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+    double cyc = 0; for (auto c : h) cyc += (double)c; cyc /= grid;
+    const double flops = 2.0 * 128 * N * 8 * 6.0 * iters * grid;
+    printf("issue rate: grid %d N %d: %.1f cycles per 128xNx8 TF32 MMA (ideal %d), %.1f TFLOP/s over %.2f ms, %.3f GHz\n", grid, N,
+           cyc / (6.0 * iters), 128 * N / 256, flops / (ms * 1e-3) * 1e-12, ms, cyc / (ms * 1e-3) * 1e-9);
+    cudaFree(d);
+}
+
 static float tf32_trunc(float x) {
     uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x;
 }
@@ -152,5 +232,6 @@ int main() {
     int bad = 0;
     for (int mode = 0; mode < 3; ++mode) { bad += run<240>(mode); bad += run<256>(mode); bad += run<16>(mode); }
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
+    run_issue_rate<240>(1); run_issue_rate<240>(148); run_issue_rate<256>(148); run_issue_rate<128>(148);
     return bad != 0;
 }
