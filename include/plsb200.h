@@ -172,6 +172,17 @@ int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, con
                         int nbt, const int32_t* cell_start, int ncell, int unit_cells, const double* pivot,
                         double* sum, double* sumsq, double* T, double* nrm2, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* rb_boot on the FP64 tensor path (DMMA): same contract as plsb200_rb_boot_f64 except that the block offsets are
+ * read on the HOST (`cell_start_host`), T may be NULL (squared norms only: first pass of the multiblock bootstrap)
+ * and designs whose blocks, each padded to a multiple of 4 rows, exceed 384 rows are not supported: the workspace
+ * query then returns 0 and the caller uses plsb200_rb_boot_f64.  Phase 1 keeps X fragments register-resident and
+ * streams packed coefficients like the K4 kernel; the latent products T = Xc . VS are a split-K DMMA GEMM.     */
+size_t plsb200_rb_boot_dmma_f64_workspace(int N, int64_t p, int K, int nbt, const int32_t* cell_start_host,
+                                          int ncell, int unit_cells, int want_t);
+int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
+                             int nbt, const int32_t* cell_start_host, int ncell, int unit_cells, const double* pivot,
+                             double* sum, double* sumsq, double* T, double* nrm2, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* multiblock glue (class_functions.py:454-516): the last `unit_cells` blocks of rb_boot are plain linear rows
  * (task part of the multiblock matrix, no standardisation).
  * scatter_coef: C[r] (N x K) = scatter(E, idx_r) written out explicitly.

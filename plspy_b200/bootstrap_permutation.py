@@ -250,7 +250,7 @@ def _boot_multiblock(eng, U, s, V, cond_order, mctype, niter, pls_alg, contrast,
     d2t, _ = eng.nspace_coef(eng.G, Ct)
     # behaviour rows: raw (un-normalised) correlation rows and pass 1 for their squared norms
     Qraw, Wb, Yz = eng.rb_coef(Ybscan, ib, st["cells_b"], np.eye(len(bcol)), scatter=True, want_yz=True)
-    _, _, _, nrm_b = eng.rb_boot(st["Xcb"], Qraw, Wb, st["cells_b"])
+    _, _, _, nrm_b = eng.rb_boot(st["Xcb"], Qraw, Wb, st["cells_b"], want_t=False)
     d2row = torch.zeros(R, K, dtype=torch.float64, device=dev)
     d2row[:, tcol_d] = d2t
     d2row[:, bcol_d] = nrm_b

@@ -1,0 +1,520 @@
+// K5 on the FP64 tensor path: the p-space bootstrap pass of behaviour / multiblock PLS (same contract as
+// plsb200_rb_boot_f64 in rb.cu, which stays as the general fallback).
+//
+// Per bootstrap b and (group, condition) cell c (class_functions.py:219-245 as called at bootstrap_permutation.py:613):
+//     P_c[v, k]  = sum_{i in c} Xc[i, v] Q_b[i, k]                      <- DMMA, M = voxels, k-dim = rows of the cell
+//     m1, m2     = sum_i w_b[i] Xc[i, v], sum_i w_b[i] Xc[i, v]^2       <- FMA on the same register-resident fragments
+//     VS_b[v, k] = sum_c P_c[v, k] / (sd_c(v) sqrt(n_c)),  sd_c^2 = m2 - m1^2   (1 for the trailing `unit` cells)
+// and then  sum / sum of squares of (VS_b - pivot),  ||VS_b[:, k]||^2  and  T_b = Xc . VS_b  (N x K).
+//
+//   kernel A (rb_vs_kernel): as K4 (boot.cu) a warp owns 8 voxels and keeps its X fragments in registers for the
+//     whole launch; the per-bootstrap coefficients are pre-packed in B-fragment order (cells padded to whole
+//     k-steps of 4 rows) and streamed through shared memory with bulk copies.  A cell is a run of k-steps; at its
+//     end the quad-reduced moments give the scale and the cell's D fragments are folded into VS.  VS_b is written
+//     transposed ([column][voxel]) for kernel B, the moments are folded in registers.
+//   kernel B (gemm_nt_partial_kernel): T = Xc . VS^T-transposed as a split-K DMMA GEMM over voxel chunks (the Gram
+//     kernel generalised to two operand matrices), partials reduced in a fixed order.
+// Columns are processed in passes of 8*NBLK (NBLK = 1, 2, 3 for K <= 8, 16, more); the running moments live in
+// shared memory so that the registers are free for up to 96 k-steps of X fragments (384 padded rows).
+#include "common.cuh"
+
+namespace plsb {
+
+constexpr int RD_WARPS = 8;
+constexpr int RD_THREADS = RD_WARPS * 32;
+constexpr int RD_VOX = RD_WARPS * 8;
+constexpr int RD_MAXKS = 96;
+
+struct RdPlan {
+    int nks, nblk, kcp, npass, nstage;
+    size_t stage_doubles;        // packed coefficients + weights of one bootstrap and one pass
+    size_t smem_bytes;
+    int krow[RD_MAXKS * 4];      // k-step slot -> row of Xc (-1 = padding)
+    double celln[16];            // rows per cell (negative for unit cells)
+    int ncell;
+    uint32_t cend[3];            // bit s set: k-step s ends a cell
+};
+
+static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, RdPlan& r) {
+    if (N < 1 || K < 1 || ncell < 1 || ncell > 16 || cs[0] != 0 || cs[ncell] != N) return false;
+    r.ncell = ncell;
+    int s = 0;
+    r.cend[0] = r.cend[1] = r.cend[2] = 0;
+    for (int c = 0; c < ncell; ++c) {
+        const int n = cs[c + 1] - cs[c];
+        if (n < 1) return false;
+        const int ks = (n + 3) / 4;
+        if (s + ks > RD_MAXKS) return false;
+        for (int t = 0; t < ks * 4; ++t) r.krow[s * 4 + t] = t < n ? cs[c] + t : -1;
+        r.celln[c] = c >= ncell - unit_cells ? -(double)n : (double)n;
+        r.cend[(s + ks - 1) >> 5] |= 1u << ((s + ks - 1) & 31);
+        s += ks;
+    }
+    r.nks = (s + 3) / 4 * 4;                       // kernels are instantiated for multiples of 4 k-steps
+    for (int t = s; t < r.nks; ++t)
+        for (int q = 0; q < 4; ++q) r.krow[t * 4 + q] = -1;
+    r.nblk = K <= 8 ? 1 : (K <= 16 ? 2 : 3);
+    r.kcp = 8 * r.nblk;
+    r.npass = (int)cdiv(K, r.kcp);
+    r.stage_doubles = (size_t)r.nks * r.nblk * 32 + (size_t)r.nks * 4;
+    const size_t fixed = ((size_t)16 + 2 * r.nblk * 2 * RD_THREADS + RD_WARPS * 16 * 16) * sizeof(double) + 256;
+    int ns = (int)((225 * 1024 - fixed) / (r.stage_doubles * sizeof(double)));
+    if (ns > 4) ns = 4;
+    if (ns < 2) return false;
+    r.nstage = ns;
+    r.smem_bytes = ns * r.stage_doubles * sizeof(double) + fixed;
+    return true;
+}
+
+// Q (R x N x K), W (R x N) -> per (bootstrap, pass): [nks][nblk][32] B-fragments (lane = 4*col + q holds
+// Q[krow[4s+q]][k0 + 8j + col]) followed by [nks][4] weights.
+__global__ void rd_pack_kernel(const double* __restrict__ Q, const double* __restrict__ W, int N, int K, int b0,
+                               const int* __restrict__ krow, int nks, int nblk, int npass,
+                               double* __restrict__ pack) {
+    const int bb = blockIdx.x, pass = blockIdx.y;
+    const size_t stage = (size_t)nks * nblk * 32 + (size_t)nks * 4;
+    double* out = pack + ((size_t)bb * npass + pass) * stage;
+    const double* q = Q + (size_t)(b0 + bb) * N * K;
+    const double* w = W ? W + (size_t)(b0 + bb) * N : nullptr;
+    const int k0 = pass * 8 * nblk;
+    const int nq = nks * nblk * 32;
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        const int lane = i & 31, j = (i >> 5) % nblk, s = (i >> 5) / nblk;
+        const int row = krow[4 * s + (lane & 3)], col = k0 + 8 * j + (lane >> 2);
+        out[i] = (row >= 0 && col < K) ? q[(size_t)row * K + col] : 0.0;
+    }
+    for (int i = threadIdx.x; i < nks * 4; i += blockDim.x) {
+        const int row = krow[i];
+        out[nq + i] = (row >= 0 && w) ? w[row] : 0.0;
+    }
+}
+
+struct RdArgs {
+    const double* Xc;
+    const double* pack;
+    const double* pivot;
+    const int* krow;
+    const double* celln;
+    double* sum;
+    double* sumsq;
+    double* VSt;       // [nbt][kcp][p]  (may be NULL when T is not wanted)
+    double* Npart;     // [nbt][kcp][tiles*8]
+    long long p;
+    int Kfull, k0, kc, nbt, npass, pass, nstage, ncell;
+    uint32_t cend[3];
+};
+
+constexpr int RD_MAXCELL = 16;
+
+// scale of one (cell, voxel): 1 / (sd sqrt(n)); same guards as rb_boot_kernel (an all-identical resampled block has
+// var == 0: nan -> 0 in the reference); unit cells (n < 0) are plain linear rows.  Called from one place only (a runtime loop), so the
+// FP64 sqrt / divide sequence exists once in the instruction stream.
+__device__ __forceinline__ double rd_scale(double m1, double m2, double n) {
+    if (n < 0.0) return 1.0;
+    const double var = m2 - m1 * m1;
+    return (var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * n) : 0.0;
+}
+
+template <int NKS, int NBLK>
+__global__ void __launch_bounds__(RD_THREADS, 1) rb_vs_kernel(const RdArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int stage_doubles = NKS * NBLK * 32 + NKS * 4;
+    constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
+    double* ring = reinterpret_cast<double*>(smraw);
+    double* celln = ring + (size_t)a.nstage * stage_doubles;      // [RD_MAXCELL] rows per cell (negative: unit cell)
+    double* acc = celln + RD_MAXCELL;                             // [2][NBLK*2][RD_THREADS] running moments
+    double* mom = acc + 2 * NBLK * 2 * RD_THREADS;                // [RD_WARPS][RD_MAXCELL][8 voxels][2] -> scale in [0]
+    uint64_t* full = reinterpret_cast<uint64_t*>(mom + RD_WARPS * RD_MAXCELL * 16);
+    uint64_t* empty = full + a.nstage;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = lane & 3, vr = lane >> 2;
+    const long long v = (long long)blockIdx.x * RD_VOX + warp * 8 + vr;
+    const bool ok = v < a.p;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, RD_WARPS); }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < RD_MAXCELL; i += RD_THREADS) celln[i] = i < a.ncell ? a.celln[i] : 0.0;
+    __syncthreads();
+
+    const size_t bstride = (size_t)a.npass * stage_doubles;       // doubles between consecutive bootstraps
+    auto issue = [&](int bb, int slot) {
+        mbar_expect_tx(full + slot, stage_bytes);
+        const char* src = reinterpret_cast<const char*>(a.pack + (size_t)bb * bstride + (size_t)a.pass * stage_doubles);
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+#pragma unroll 1
+        for (uint32_t off = 0; off < stage_bytes; off += 16384u)
+            bulk_g2s(dst + off, src + off, min(16384u, stage_bytes - off), full + slot);
+    };
+    if (tid == 0)
+        for (int bb = 0; bb < min(a.nstage, a.nbt); ++bb) issue(bb, bb);
+
+    double x[NKS];
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        const int row = __ldg(a.krow + 4 * s + q);
+        x[s] = (row >= 0 && ok) ? __ldg(a.Xc + (long long)row * a.p + v) : 0.0;
+    }
+    // running moments live in shared memory (one slot per thread and fragment element): registers are for X
+    double* my1 = acc + tid;
+    double* my2 = acc + NBLK * 2 * RD_THREADS + tid;
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = 8 * j + 2 * q + e;
+            const bool live = ok && c < a.kc;
+            my1[(2 * j + e) * RD_THREADS] = live ? a.sum[v * a.Kfull + a.k0 + c] : 0.0;
+            my2[(2 * j + e) * RD_THREADS] = live ? a.sumsq[v * a.Kfull + a.k0 + c] : 0.0;
+        }
+    double* wm = mom + warp * (RD_MAXCELL * 16);                  // this warp's (cell, voxel) table
+    if (warp >= 4) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the two warps of a sub-partition (see boot.cu)
+
+    int slot = 0, prev_slot = 0;
+    uint32_t phase = 0, prev_phase = 0;
+    for (int bb = 0; bb < a.nbt; ++bb) {
+        if (tid == 0 && bb > 0) {
+            const int nx = bb - 1 + a.nstage;
+            if (nx < a.nbt) { mbar_wait(empty + prev_slot, prev_phase); issue(nx, prev_slot); }
+        }
+        __syncwarp();
+        mbar_wait(full + slot, phase);
+        const volatile double* bs = ring + (size_t)slot * stage_doubles + lane;
+        const volatile double* ws = ring + (size_t)slot * stage_doubles + NKS * NBLK * 32 + q;
+
+        // ---- pass 1: weighted block moments m1 = sum w x, m2 = sum w x^2 per cell (FMA on the resident fragments)
+        {
+            double m1 = 0.0, m2 = 0.0;
+            int cell = 0;
+#pragma unroll
+            for (int s = 0; s < NKS; ++s) {
+                const double wx = ws[4 * s] * x[s];
+                m1 += wx;
+                m2 = fma(wx, x[s], m2);
+                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {        // warp-uniform: last k-step of a cell
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+                    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+                    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+                    if (q == 0) { wm[(cell * 8 + vr) * 2] = m1; wm[(cell * 8 + vr) * 2 + 1] = m2; }
+                    ++cell;
+                    m1 = m2 = 0.0;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- scales: one (cell, voxel) pair per lane, no redundancy across the quad
+        for (int i = lane; i < a.ncell * 8; i += 32) {
+            const double sc = rd_scale(wm[2 * i], wm[2 * i + 1], celln[i >> 3]);
+            wm[2 * i] = sc;
+        }
+        __syncwarp();
+
+        // ---- pass 2: P_c = X_c^T Q_c on the tensor cores, folded into VS with the cell's scale
+        double d[NBLK][2], vs[NBLK][2];
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j) { d[j][0] = d[j][1] = 0.0; vs[j][0] = vs[j][1] = 0.0; }
+        {
+            int cell = 0;
+#pragma unroll
+            for (int s = 0; s < NKS; ++s) {
+#pragma unroll
+                for (int j = 0; j < NBLK; ++j) {
+                    const double b = bs[(s * NBLK + j) * 32];
+                    dmma884(d[j][0], d[j][1], x[s], b);
+                }
+                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {
+                    const double sc = wm[(cell * 8 + vr) * 2];
+                    ++cell;
+#pragma unroll
+                    for (int j = 0; j < NBLK; ++j) {
+                        vs[j][0] = fma(sc, d[j][0], vs[j][0]);
+                        vs[j][1] = fma(sc, d[j][1], vs[j][1]);
+                        d[j][0] = d[j][1] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+
+        // ---- fold: moments, squared column norms (this warp's 8 voxels), transposed VS for the latent GEMM
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * j + 2 * q + e;
+                const double val = ok ? vs[j][e] : 0.0;
+                const double pv = (ok && a.pivot && c < a.kc) ? __ldg(a.pivot + v * a.Kfull + a.k0 + c) : 0.0;
+                const double dd = val - pv;
+                my1[(2 * j + e) * RD_THREADS] += dd;
+                my2[(2 * j + e) * RD_THREADS] = fma(dd, dd, my2[(2 * j + e) * RD_THREADS]);
+                double n2 = val * val;
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
+                if (vr == 0)
+                    a.Npart[((size_t)bb * (8 * NBLK) + c) * ((size_t)gridDim.x * RD_WARPS) + blockIdx.x * RD_WARPS + warp] = n2;
+                if (a.VSt && ok) a.VSt[((size_t)bb * (8 * NBLK) + c) * a.p + v] = val;
+            }
+        prev_slot = slot; prev_phase = phase;
+        if (++slot == a.nstage) { slot = 0; phase ^= 1u; }
+    }
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * j + 2 * q + e;
+                if (c < a.kc) {
+                    a.sum[v * a.Kfull + a.k0 + c] = my1[(2 * j + e) * RD_THREADS];
+                    a.sumsq[v * a.Kfull + a.k0 + c] = my2[(2 * j + e) * RD_THREADS];
+                }
+            }
+    }
+}
+
+// nrm2[b0 + bb][k0 + c] = sum over the (tile, warp) partials: one warp per output, lanes stride over the contiguous
+// partials, fixed-order shuffle tree (deterministic)
+__global__ void rd_norm_reduce_kernel(const double* __restrict__ Npart, int nparts, int nbt, int kcp, int kc, int K, int k0,
+                                      double* __restrict__ nrm2) {
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= nbt * kc) return;
+    const int bb = o / kc, c = o % kc;
+    const double* src = Npart + ((size_t)bb * kcp + c) * nparts;
+    double s = 0.0;
+    for (int t = lane; t < nparts; t += 32) s += src[t];
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+    if (lane == 0) nrm2[(size_t)bb * K + k0 + c] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C[NA x NB] = A[NA x p] . B[NB x p]^T, both row-major (voxels contiguous), FP64 DMMA, split over voxel chunks.
+// Same tiling as the Gram kernel (64 x 64 output tiles, 32-voxel stages, 3-stage cp.async ring).
+constexpr int GN_T = 64, GN_KC = 32, GN_STR = GN_KC + 4, GN_STAGES = 3, GN_THREADS = 128;
+
+template <int VEC>   // doubles per cp.async (2 when every row start is 16-byte aligned, else 1)
+__global__ void __launch_bounds__(GN_THREADS) gemm_nt_partial_kernel(const double* __restrict__ A, int NA, long long lda,
+                                                                    const double* __restrict__ B, int NB, long long ldb,
+                                                                    long long p, long long chunk, int ntb,
+                                                                    double* __restrict__ part) {
+    extern __shared__ __align__(16) double sm[];
+    const int ti = blockIdx.x / ntb, tj = blockIdx.x % ntb;
+    const long long v0 = (long long)blockIdx.y * chunk;
+    const long long v1 = min(p, v0 + chunk);
+    const int nst = (int)((v1 - v0 + GN_KC - 1) / GN_KC);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;
+    double* As = sm;
+    double* Bs = sm + GN_STAGES * GN_T * GN_STR;
+    auto load_stage = [&](int st, int kt) {
+        const long long vb = v0 + (long long)kt * GN_KC;
+        constexpr int CH = GN_KC / VEC;
+        for (int c = tid; c < GN_T * CH; c += GN_THREADS) {
+            const int r = c / CH, cc = (c % CH) * VEC;
+            const long long vv = vb + cc;
+            long long left = v1 - vv; if (left < 0) left = 0; if (left > VEC) left = VEC;
+            {
+                const int row = ti * GN_T + r;
+                const int nb = row < NA ? (int)left * 8 : 0;
+                cp_async_zfill<VEC * 8>(As + (st * GN_T + r) * GN_STR + cc, nb ? A + (long long)row * lda + vv : A, nb);
+            }
+            {
+                const int row = tj * GN_T + r;
+                const int nb = row < NB ? (int)left * 8 : 0;
+                cp_async_zfill<VEC * 8>(Bs + (st * GN_T + r) * GN_STR + cc, nb ? B + (long long)row * ldb + vv : B, nb);
+            }
+        }
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < GN_STAGES - 1; ++s) {
+        if (s < nst) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < nst; ++kt) {
+        cp_async_wait<GN_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kt + GN_STAGES - 1;
+            if (nk < nst) load_stage(nk % GN_STAGES, nk);
+            cp_async_commit();
+        }
+        const int st = kt % GN_STAGES;
+        const double* a_base = As + (st * GN_T + wi + fr) * GN_STR + fk;
+        const double* b_base = Bs + (st * GN_T + wj + fr) * GN_STR + fk;
+#pragma unroll
+        for (int ks = 0; ks < GN_KC / 4; ++ks) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { af[t] = a_base[t * 8 * GN_STR + ks * 4]; bf[t] = b_base[t * 8 * GN_STR + ks * 4]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+        }
+    }
+    cp_async_wait<0>();
+    double* out = part + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * (GN_T * GN_T);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int r = wi + x * 8 + fr, c = wj + y * 8 + 2 * fk;
+            *reinterpret_cast<double2*>(out + r * GN_T + c) = make_double2(acc[x][y][0], acc[x][y][1]);
+        }
+}
+
+// T[b0 + bb][i][k0 + c] = sum over voxel chunks of C[i][bb*kcp + c]
+__global__ void rd_latent_reduce_kernel(const double* __restrict__ part, int ntiles, int ntb, int nsplit, int N, int nbt,
+                                        int kcp, int kc, int K, int k0, double* __restrict__ T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nbt * N * kc) return;
+    const int c = (int)(i % kc), row = (int)((i / kc) % N), bb = (int)(i / ((long long)kc * N));
+    const int col = bb * kcp + c;
+    const int tile = (row / GN_T) * ntb + col / GN_T, e = (row % GN_T) * GN_T + col % GN_T;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[((long long)sp * ntiles + tile) * (GN_T * GN_T) + e];
+    T[((size_t)bb * N + row) * K + k0 + c] = s;
+}
+
+struct RdLayout {
+    size_t off_krow, off_celln, off_pack, off_vst, off_npart, off_gpart, total;
+    int ntile, nta, ntb, nsplit;
+    long long chunk;
+};
+
+static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_t) {
+    RdLayout L;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = 0;
+    L.off_krow = o; o = al(o + (size_t)r.nks * 4 * sizeof(int));
+    L.off_celln = o; o = al(o + 16 * sizeof(double));
+    L.off_pack = o; o = al(o + (size_t)nbt * r.npass * r.stage_doubles * sizeof(double));
+    L.ntile = (int)cdiv(p, RD_VOX);
+    L.off_vst = o; if (want_t) o = al(o + (size_t)nbt * r.kcp * p * sizeof(double));
+    L.off_npart = o; o = al(o + (size_t)L.ntile * RD_WARPS * nbt * r.kcp * sizeof(double));
+    L.nta = (int)cdiv(N, GN_T); L.ntb = (int)cdiv((int64_t)nbt * r.kcp, GN_T);
+    const int64_t nk = cdiv(p, GN_KC);
+    int64_t ns = cdiv(4LL * num_sms(), (int64_t)L.nta * L.ntb);
+    const int64_t max_ns = nk / 8 > 0 ? nk / 8 : 1;
+    if (ns > max_ns) ns = max_ns;
+    if (ns < 1) ns = 1;
+    L.chunk = cdiv(nk, ns) * GN_KC;
+    L.nsplit = (int)cdiv(p, L.chunk);
+    L.off_gpart = o; if (want_t) o = al(o + (size_t)L.nsplit * L.nta * L.ntb * GN_T * GN_T * sizeof(double));
+    L.total = o;
+    return L;
+}
+
+template <int NKS, int NBLK>
+static int launch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
+    rb_vs_kernel<NKS, NBLK><<<ntile, RD_THREADS, r.smem_bytes, st>>>(a);
+    PLSB_LAUNCH_CHECK("rb_vs_kernel");
+    return PLSB200_OK;
+}
+
+template <int NBLK>
+static int dispatch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
+    switch (r.nks) {
+#define PLSB_CASE(n) case n: return launch_vs<n, NBLK>(r, a, ntile, st);
+        PLSB_CASE(4) PLSB_CASE(8) PLSB_CASE(12) PLSB_CASE(16) PLSB_CASE(20) PLSB_CASE(24) PLSB_CASE(28) PLSB_CASE(32)
+        PLSB_CASE(36) PLSB_CASE(40) PLSB_CASE(44) PLSB_CASE(48) PLSB_CASE(52) PLSB_CASE(56) PLSB_CASE(60) PLSB_CASE(64)
+        PLSB_CASE(68) PLSB_CASE(72) PLSB_CASE(76) PLSB_CASE(80)
+        PLSB_CASE(84) PLSB_CASE(88) PLSB_CASE(92) PLSB_CASE(96)
+#undef PLSB_CASE
+        default: break;
+    }
+    set_err("rb_boot_dmma_f64: no kernel for %d k-steps x %d column blocks", r.nks, NBLK);
+    return PLSB200_EUNSUPPORTED;
+}
+
+}  // namespace plsb
+
+using namespace plsb;
+
+// cell_start_host: ncell+1 row offsets in HOST memory.  Returns 0 when the design is outside what the DMMA path is
+// built for (more than 96 k-steps of 4 rows after padding every cell to a multiple of 4): use plsb200_rb_boot_f64.
+extern "C" size_t plsb200_rb_boot_dmma_f64_workspace(int N, int64_t p, int K, int nbt, const int32_t* cell_start_host,
+                                                     int ncell, int unit_cells, int want_t) {
+    RdPlan r;
+    if (!cell_start_host || p < 1 || nbt < 1 || !rd_plan(N, K, cell_start_host, ncell, unit_cells, r)) return 0;
+    return rd_layout(r, N, p, nbt, want_t != 0).total;
+}
+
+extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K,
+                                        int b0, int nbt, const int32_t* cell_start_host, int ncell, int unit_cells,
+                                        const double* pivot, double* sum, double* sumsq, double* T, double* nrm2,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    PLSB_CHECK_ARG(Xc && Q && cell_start_host && sum && sumsq && nrm2 && workspace, "rb_boot_dmma_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && nbt > 0 && ncell > 0, "rb_boot_dmma_f64: bad shape");
+    RdPlan r;
+    if (!rd_plan(N, K, cell_start_host, ncell, unit_cells, r)) {
+        set_err("rb_boot_dmma_f64: design not supported (N=%d, %d cells): use rb_boot_f64", N, ncell);
+        return PLSB200_EUNSUPPORTED;
+    }
+    const bool want_t = T != nullptr;
+    const RdLayout L = rd_layout(r, N, p, nbt, want_t);
+    if (workspace_bytes < L.total) {
+        set_err("rb_boot_dmma_f64: workspace %zu < %zu bytes", workspace_bytes, L.total);
+        return PLSB200_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    int* d_krow = (int*)(ws + L.off_krow);
+    double* d_celln = (double*)(ws + L.off_celln);
+    double* d_pack = (double*)(ws + L.off_pack);
+    double* d_vst = want_t ? (double*)(ws + L.off_vst) : nullptr;
+    double* d_npart = (double*)(ws + L.off_npart);
+    double* d_gpart = (double*)(ws + L.off_gpart);
+    PLSB_CUDA(cudaMemcpyAsync(d_krow, r.krow, (size_t)r.nks * 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+    PLSB_CUDA(cudaMemcpyAsync(d_celln, r.celln, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rd_pack_kernel<<<dim3(nbt, r.npass), 256, 0, st>>>(Q, W, N, K, b0, d_krow, r.nks, r.nblk, r.npass, d_pack);
+    PLSB_LAUNCH_CHECK("rd_pack_kernel");
+    for (int pass = 0; pass < r.npass; ++pass) {
+        RdArgs a;
+        a.Xc = Xc; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
+        a.VSt = d_vst; a.Npart = d_npart; a.p = p; a.Kfull = K; a.k0 = pass * r.kcp;
+        a.kc = K - a.k0 < r.kcp ? K - a.k0 : r.kcp;
+        a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell;
+        a.cend[0] = r.cend[0]; a.cend[1] = r.cend[1]; a.cend[2] = r.cend[2];
+        int rc;
+        switch (r.nblk) {
+            case 1: rc = dispatch_vs<1>(r, a, L.ntile, st); break;
+            case 2: rc = dispatch_vs<2>(r, a, L.ntile, st); break;
+            default: rc = dispatch_vs<3>(r, a, L.ntile, st); break;
+        }
+        if (rc != PLSB200_OK) return rc;
+        rd_norm_reduce_kernel<<<(unsigned)cdiv((int64_t)nbt * a.kc * 32, 256), 256, 0, st>>>(
+            d_npart, L.ntile * RD_WARPS, nbt, r.kcp, a.kc, K, a.k0, nrm2 + (size_t)b0 * K);
+        PLSB_LAUNCH_CHECK("rd_norm_reduce_kernel");
+        if (want_t) {
+            const size_t smem = (size_t)2 * GN_STAGES * GN_T * GN_STR * sizeof(double);
+            dim3 grid((unsigned)(L.nta * L.ntb), (unsigned)L.nsplit);
+            const bool vec2 = (p % 2 == 0) && ((reinterpret_cast<uintptr_t>(Xc) & 15) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(d_vst) & 15) == 0);
+            if (vec2) {
+                PLSB_CUDA(cudaFuncSetAttribute(gemm_nt_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gemm_nt_partial_kernel<2><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
+            } else {
+                PLSB_CUDA(cudaFuncSetAttribute(gemm_nt_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gemm_nt_partial_kernel<1><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
+            }
+            PLSB_LAUNCH_CHECK("gemm_nt_partial_kernel");
+            const long long n = (long long)nbt * N * a.kc;
+            rd_latent_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(d_gpart, L.nta * L.ntb, L.ntb, L.nsplit, N, nbt,
+                                                                             r.kcp, a.kc, K, a.k0, T + (size_t)b0 * N * K);
+            PLSB_LAUNCH_CHECK("rd_latent_reduce_kernel");
+        }
+    }
+    return PLSB200_OK;
+}

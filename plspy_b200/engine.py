@@ -381,30 +381,55 @@ class Engine:
                                           self._stream()), "rb_coef_f64")
         return Q, W, Yz
 
-    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, unit_cells=0, max_ws_bytes=512 << 20):
+    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, unit_cells=0, max_ws_bytes=2 << 30, want_t=True):
         """p-space pass over all bootstraps in Q: returns (sum, sumsq) of VS - pivot (p x K),
-        T (R x N x K) = Xc @ VS_b and nrm2 (R x K)."""
-        cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)
+        T (R x N x K) = Xc @ VS_b (None when want_t is False) and nrm2 (R x K).
+        Runs on the FP64 tensor path (plsb200_rb_boot_dmma_f64) when the design fits its register-resident
+        fragments, else on the general FMA kernel."""
+        cs_host = np.ascontiguousarray(np.asarray(cell_start, dtype=np.int32))
         R, N, K = int(Q.shape[0]), int(Q.shape[1]), int(Q.shape[2])
         p = int(Xc.shape[1])
+        ncell = int(cs_host.size) - 1
         s1 = torch.zeros(p, K, dtype=F64, device=self.device); s2 = torch.zeros_like(s1)
-        T = self._empty(R, N, K); nrm2 = self._empty(R, K)
+        T = self._empty(R, N, K) if want_t else None
+        nrm2 = self._empty(R, K)
         if pivot is not None:
             pivot = self.to_device(pivot, F64)
+        Xc = Xc.contiguous()
+        per = lib.plsb200_rb_boot_dmma_f64_workspace(N, p, K, 1, cs_host.ctypes.data, ncell, int(unit_cells),
+                                                     int(want_t))
+        if per and not getattr(self, "force_rb_fma", False):
+            nbt = max(1, min(R, int(max_ws_bytes // per)))
+            ws_bytes = lib.plsb200_rb_boot_dmma_f64_workspace(N, p, K, nbt, cs_host.ctypes.data, ncell,
+                                                              int(unit_cells), int(want_t))
+            with torch.cuda.device(self.device):
+                ws = self._ws(ws_bytes)
+                self._mark("rb_boot")
+                for b0 in range(0, R, nbt):
+                    n = min(nbt, R - b0)
+                    check(lib.plsb200_rb_boot_dmma_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n,
+                                                       cs_host.ctypes.data, ncell, int(unit_cells), self._p(pivot),
+                                                       self._p(s1), self._p(s2), self._p(T), self._p(nrm2),
+                                                       self._p(ws), ws.numel(), self._stream()), "rb_boot_dmma_f64")
+                self._mark("rb_boot")
+            return s1, s2, T, nrm2
+        cs = self.to_device(cs_host, I32)
+        if T is None:
+            T = self._empty(R, N, K)
         per = lib.plsb200_rb_boot_f64_workspace(N, p, K, 1)
-        nbt = max(1, min(R, int(max_ws_bytes // max(per, 1))))
+        nbt = max(1, min(R, int(min(max_ws_bytes, 512 << 20) // max(per, 1))))
         with torch.cuda.device(self.device):
             ws = self._ws(per * nbt)
             self._mark("rb_boot")
             for b0 in range(0, R, nbt):
                 n = min(nbt, R - b0)
                 check(lib.plsb200_rb_boot_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n, self._p(cs),
-                                              int(cs.numel()) - 1, int(unit_cells), self._p(pivot), self._p(s1),
+                                              ncell, int(unit_cells), self._p(pivot), self._p(s1),
                                               self._p(s2),
                                               self._p(T), self._p(nrm2), self._p(ws), ws.numel(), self._stream()),
                       "rb_boot_f64")
             self._mark("rb_boot")
-        return s1, s2, T, nrm2
+        return s1, s2, (T if want_t else None), nrm2
 
     def rb_lvcorr(self, T, nrm2, Yz, idx, cell_start, nb):
         cs = self.to_device(np.asarray(cell_start, dtype=np.int32), I32)

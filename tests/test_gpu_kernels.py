@@ -244,3 +244,54 @@ def test_split_gram_and_svd(torch_cuda):
         np.testing.assert_allclose(np.diag(st[s]), np.diag(test), rtol=1e-8, atol=1e-9)      # diagonal is sign-free
         np.testing.assert_allclose(np.abs(ur[s]), np.abs(V1t @ V2t.T), rtol=1e-8, atol=1e-9)
         np.testing.assert_allclose(np.abs(vr[s]), np.abs(U1.T @ U2), rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("cells,unit,p,K,R", [
+    ([20] * 6, 0, 1000, 24, 9),          # cfg 2 design (rb): 6 blocks of 20 rows, 3 column blocks
+    ([7, 9, 8, 5], 0, 333, 5, 6),        # ragged blocks (padding rows inside k-steps), odd p, one column block
+    ([30] * 4, 0, 500, 16, 5),           # multiblock pass 1: raw behaviour rows, two column blocks
+    ([30] * 4 + [240], 1, 700, 24, 4),   # multiblock pass 2: 92 k-steps -> 2 column blocks per pass, unit block
+    ([3, 2], 0, 64, 2, 3),               # tiny
+])
+def test_rb_boot_dmma_matches_fma_kernel_and_numpy(torch_cuda, cells, unit, p, K, R):
+    """the DMMA bootstrap pass (rb_dmma.cu) against the general FMA kernel (rb.cu) and float64 numpy"""
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(len(cells) * 100 + K)
+    cs = np.concatenate(([0], np.cumsum(cells))).astype(np.int32)
+    N = int(cs[-1])
+    Xc = rs.standard_normal((N, p))
+    Q = rs.standard_normal((R, N, K)) / np.sqrt(N)
+    W = np.zeros((R, N))
+    for r in range(R):
+        for c in range(len(cells)):
+            cnt = np.bincount(rs.randint(0, cells[c], cells[c]), minlength=cells[c])
+            W[r, cs[c]:cs[c + 1]] = cnt / cells[c]
+    pivot = rs.standard_normal((p, K))
+    eng = Engine(Xc)
+    Qd = eng.to_device(Q, torch_cuda.float64); Wd = eng.to_device(W, torch_cuda.float64)
+    out = {}
+    for mode in ("dmma", "fma"):
+        eng.force_rb_fma = mode == "fma"
+        out[mode] = [t.cpu().numpy() for t in eng.rb_boot(eng.X, Qd, Wd, cs, pivot=pivot, unit_cells=unit)]
+    # numpy reference
+    VS = np.zeros((R, p, K))
+    for r in range(R):
+        for c in range(len(cells)):
+            x = Xc[cs[c]:cs[c + 1]]; w = W[r, cs[c]:cs[c + 1]][:, None]
+            P = x.T @ Q[r, cs[c]:cs[c + 1]]
+            if c >= len(cells) - unit:
+                VS[r] += P
+            else:
+                var = (w * x * x).sum(0) - ((w * x).sum(0)) ** 2
+                sc = np.where(var > 1e-13 * (w * x * x).sum(0), 1.0 / np.sqrt(np.maximum(var, 1e-300) * cells[c]), 0.0)
+                VS[r] += sc[:, None] * P
+    d = VS - pivot
+    ref = [d.sum(0), (d ** 2).sum(0), np.einsum("ip,rpk->rik", Xc, VS), (VS ** 2).sum(1)]
+    for name, got in out.items():
+        for g, want in zip(got, ref):
+            np.testing.assert_allclose(g, want, rtol=1e-9, atol=1e-9 * np.abs(want).max(), err_msg=name)
+    # want_t=False (multiblock first pass) gives the same norms
+    eng.force_rb_fma = False
+    _, _, T0, n0 = eng.rb_boot(eng.X, Qd, Wd, cs, unit_cells=unit, want_t=False)
+    assert T0 is None
+    np.testing.assert_allclose(n0.cpu().numpy(), ref[3], rtol=1e-9)
