@@ -57,19 +57,20 @@ def workload_name(groups, C, p, nperm, nboot):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock, power and clock-event reasons of one GPU from a thread of this process through NVML
-    (nvidia_ml_py) every `period` seconds.  An external `nvidia-smi -lms` process was measurably disturbing the
-    timed region (its start-up holds the driver for tens of ms), so it is only the fallback when NVML cannot be
-    loaded; in that case it is started well before the timed region."""
+    """SM clock, power and clock-event reasons of one GPU through NVML (nvidia_ml_py), sampled from the MAIN thread
+    once per step at the moment the dominant kernel has just been launched (the engine's `on_mark` hook), i.e.
+    while the GPU is under load and the host has nothing else to do.  Polling from a second thread or from an
+    external `nvidia-smi -lms` process measurably disturbed the timed region (isolated steps stalled by 20-130 ms
+    when a query coincided with the step's own driver calls), so neither is used; nvidia-smi remains the fallback
+    when NVML cannot be loaded and is then started well before the timed region."""
 
     NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
              ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
              ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
              ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
 
-    def __init__(self, gpu_index, period=0.05):
-        import threading
-        self.rows, self.period, self._stop, self._on = [], period, threading.Event(), threading.Event()
+    def __init__(self, gpu_index):
+        self.rows, self._on, self._n = [], False, 0
         self.nv = self.h = self.proc = self.path = None
         self.gpu_index = gpu_index
         try:
@@ -77,13 +78,13 @@ class ClockSampler:
             pynvml.nvmlInit()
             # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
             import torch
-            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
-                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            props = torch.cuda.get_device_properties(gpu_index)
+            bus = getattr(props, "pci_bus_id", None)
             self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index) if bus is None else self._by_bus(pynvml, gpu_index, bus)
             self.nv = pynvml
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
+            self.sample(force=True)      # first queries are slow (lazy initialisation): keep them out of the timed region
+            self.rows.clear()
         except Exception:  # noqa: BLE001
             self.nv = None
             self.proc, self.path = _smi_start(gpu_index)
@@ -97,38 +98,44 @@ class ClockSampler:
                 return h
         return nv.nvmlDeviceGetHandleByIndex(idx)
 
-    def _run(self):
+    def sample(self, force=False):
+        if self.nv is None or not (self._on or force):
+            return
         nv = self.nv
-        while not self._stop.is_set():
-            if self._on.is_set():
-                try:
-                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
-                                      nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
-                                      int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
-                except Exception:  # noqa: BLE001
-                    pass
-            self._stop.wait(self.period)
+        try:
+            self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                              nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                              int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def on_mark(self, name):
+        """Engine hook: called before and after the launch of a marked kernel; sample after the launch."""
+        if name == "boot_moments":
+            self._n += 1
+            if self._n % 2 == 0:
+                self.sample()
 
     def begin(self):
         if self.nv is None and self.proc is None:
             self.proc, self.path = _smi_start(self.gpu_index)
             time.sleep(1.0)
         self.rows.clear()
-        self._on.set()
+        self._n = 0
+        self._on = True
 
     def end(self):
-        self._on.clear()
+        self._on = False
         if self.nv is None:
             out = _smi_stop(self.proc, self.path)
             self.proc = None
             return out
-        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "source": "nvml in-process, 50 ms period"}
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [],
+               "source": "nvml, main thread, one sample per step while the dominant kernel runs"}
         rows = list(self.rows)
         if rows:
-            pmax = max(r[1] for r in rows)
-            busy = [r[0] for r in rows if r[1] > 0.5 * pmax] or [r[0] for r in rows]
-            out["sm_mhz"] = statistics.median(busy)
-            out["power_w_max"] = pmax
+            out["sm_mhz"] = statistics.median(r[0] for r in rows)
+            out["power_w_max"] = max(r[1] for r in rows)
             out["samples"] = len(rows)
             for name, attr in self.NAMES:
                 bit = getattr(self.nv, attr, 0)
@@ -137,7 +144,7 @@ class ClockSampler:
         return out
 
     def close(self):
-        self._stop.set()
+        pass
 
 
 def _smi_start(gpu_index):
@@ -285,9 +292,13 @@ def run_gpu(args):
     Xd, Vd, gpd, gbd = Xh.to(dev), Vh.to(dev), gph.to(dev), gbh.to(dev)
     torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+
     def one_pass(Xa, Va, pa, ba, events=None, precision="fp64"):
         eng = Engine(Xa, device=dev, precision=precision)            # Gram (and TF32 planes) recomputed every step
         eng.kernel_events = events
+        if events is not None and sampler is not None:
+            eng.on_mark = sampler.on_mark
         rt = bp.ResampleTest._create("mct", Xa, None, U, s.copy(), Va, co, MCTYPE, preprocess=cf._mean_centre,
                                      nperm=nperm * world, nboot=nboot * world, Tvsc_orig=Tvsc, CI=0.95,
                                      perm_indices=pa, boot_indices=ba, engine=eng)
@@ -314,8 +325,6 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
-
-    sampler = ClockSampler(local) if rank == 0 else None
 
     def measure(precision):
         """value arm (inputs resident in HBM) and e2e arm (pinned host buffers in, host results out) for one
@@ -455,7 +464,7 @@ def main():
     ap.add_argument("--voxels", type=int, default=P_VOX)
     ap.add_argument("--perms", type=int, default=NPERM)
     ap.add_argument("--boots", type=int, default=NBOOT)
-    ap.add_argument("--ref-sample", type=int, default=6, help="perms and boots per CPU-baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=20, help="perms and boots per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32x3"],
                     help="fp64 = exact mode (headline); tf32x3 = fast mode only")

@@ -48,6 +48,7 @@ class Engine:
         self.ldx = int(self.X.stride(0))
         self._G = None
         self.kernel_events = None     # set to {} to record CUDA events around named kernels (bench.py)
+        self.on_mark = None           # optional callable(name) invoked at every _mark (bench.py: clock sampling)
         self.h2d_bytes = self.X.numel() * 8 if not (torch.is_tensor(X) and X.is_cuda) else 0
 
     # ------------------------------------------------------------------ plumbing
@@ -106,6 +107,8 @@ class Engine:
         """CUDA event on the launching stream, kept only when kernel_events is enabled."""
         if self.kernel_events is None:
             return
+        if self.on_mark is not None:
+            self.on_mark(name)
         ev = torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream(self.device))
         self.kernel_events.setdefault(name, []).append(ev)
