@@ -26,11 +26,25 @@ def _deps():
     return d
 
 
+STAMP = OUT + ".srchash"
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(_deps()):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def up_to_date():
-    if not os.path.exists(OUT):
+    """The library is current when the hash of all sources recorded at build time matches (file times are not
+    reliable after the tree has been copied to another machine)."""
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(f) <= t for f in _deps())
+    return open(STAMP).read().strip() == _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -53,6 +67,8 @@ def build(force=False, verbose=False):
         if pr.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-lcudart"])
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return OUT
 
 

@@ -8,6 +8,8 @@ from plspy_b200.engine import Engine
 ap = argparse.ArgumentParser(); ap.add_argument("--cfg", type=int, default=2)
 ap.add_argument("--iters", type=float, default=1.0, help="scale factor on the iteration counts")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--precision", default="fp64")
+ap.add_argument("--draw", action="store_true", help="let PLS() draw its own indices (native generator) instead of passing them in")
 a = ap.parse_args()
 rs = np.random.RandomState(20260000 + a.cfg)
 if a.cfg == 2:
@@ -16,6 +18,8 @@ elif a.cfg == 1:
     method, groups, C, p, nb, P, B = "mct", (10, 10), 3, 10000, 0, 500, 500
 elif a.cfg == 3:
     method, groups, C, p, nb, P, B = "cst", (25, 25, 25), 4, 200000, 0, 5000, 5000
+elif a.cfg == 30:    # the north-star target ("cfg 3m"): mct on the cfg-3 design
+    method, groups, C, p, nb, P, B = "mct", (25, 25, 25), 4, 200000, 0, 5000, 5000
 elif a.cfg == 4:
     method, groups, C, p, nb, P, B = "mb", (30, 30), 4, 200000, 4, 2000, 2000
 S = 500 if a.cfg == 4 else 0
@@ -41,7 +45,11 @@ out = {"cfg": a.cfg, "method": method, "index_generation_s": t_idx}
 from plspy_b200 import _lib
 for rep in range(a.reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = plspy_b200.PLS(X, groups, C, perm_indices=pi, boot_indices=bi, **kw)
+    if a.draw:
+        np.random.seed(99)
+        res = plspy_b200.PLS(X, groups, C, precision=a.precision, **kw)
+    else:
+        res = plspy_b200.PLS(X, groups, C, perm_indices=pi, boot_indices=bi, precision=a.precision, **kw)
     torch.cuda.synchronize(); out[f"pls_call_s_{rep}"] = time.perf_counter() - t0
 out["iters"] = [P, B, S]
 out["resamples_per_s_e2e"] = (P + B + 4 * S) / out[f"pls_call_s_{a.reps - 1}"]
