@@ -20,13 +20,10 @@
 
 namespace plsb {
 
-constexpr int RD_WARPS = 8;
-constexpr int RD_THREADS = RD_WARPS * 32;
-constexpr int RD_VOX = RD_WARPS * 8;
 constexpr int RD_MAXKS = 96;
 
 struct RdPlan {
-    int nks, nblk, kcp, npass, nstage;
+    int nks, nblk, kcp, npass, nstage, warps;
     size_t stage_doubles;        // packed coefficients + weights of one bootstrap and one pass
     size_t smem_bytes;
     int krow[RD_MAXKS * 4];      // k-step slot -> row of Xc (-1 = padding)
@@ -57,7 +54,8 @@ static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, 
     r.kcp = 8 * r.nblk;
     r.npass = (int)cdiv(K, r.kcp);
     r.stage_doubles = (size_t)r.nks * r.nblk * 32 + (size_t)r.nks * 4;
-    const size_t fixed = ((size_t)16 + 2 * r.nblk * 2 * RD_THREADS + RD_WARPS * 16 * 16) * sizeof(double) + 256;
+    r.warps = r.nks <= 32 ? 16 : 8;
+    const size_t fixed = ((size_t)16 + 2 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 16) * sizeof(double) + 256;
     int ns = (int)((225 * 1024 - fixed) / (r.stage_doubles * sizeof(double)));
     if (ns > 4) ns = 4;
     if (ns < 2) return false;
@@ -115,8 +113,11 @@ __device__ __forceinline__ double rd_scale(double m1, double m2, double n) {
     return (var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * n) : 0.0;
 }
 
-template <int NKS, int NBLK>
-__global__ void __launch_bounds__(RD_THREADS, 1) rb_vs_kernel(const RdArgs a) {
+// W = warps per CTA: 8 (256 registers per thread: up to 96 k-steps of fragments) or 16 (128 registers: <= 32 k-steps,
+// twice the warps per scheduler to hide the serial phases between the DMMA bursts).
+template <int NKS, int NBLK, int W>
+__global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
+    constexpr int RD_WARPS = W, RD_THREADS = W * 32, RD_VOX = W * 8;
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int stage_doubles = NKS * NBLK * 32 + NKS * 4;
     constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) rb_vs_kernel(const RdArgs a) {
             my2[(2 * j + e) * RD_THREADS] = live ? a.sumsq[v * a.Kfull + a.k0 + c] : 0.0;
         }
     double* wm = mom + warp * (RD_MAXCELL * 16);                  // this warp's (cell, voxel) table
-    if (warp >= 4) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the two warps of a sub-partition (see boot.cu)
+    if ((warp >> 2) & 1) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the two warps of a sub-partition (see boot.cu)
 
     int slot = 0, prev_slot = 0;
     uint32_t phase = 0, prev_phase = 0;
@@ -399,9 +400,9 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     L.off_krow = o; o = al(o + (size_t)r.nks * 4 * sizeof(int));
     L.off_celln = o; o = al(o + 16 * sizeof(double));
     L.off_pack = o; o = al(o + (size_t)nbt * r.npass * r.stage_doubles * sizeof(double));
-    L.ntile = (int)cdiv(p, RD_VOX);
+    L.ntile = (int)cdiv(p, r.warps * 8);
     L.off_vst = o; if (want_t) o = al(o + (size_t)nbt * r.kcp * p * sizeof(double));
-    L.off_npart = o; o = al(o + (size_t)L.ntile * RD_WARPS * nbt * r.kcp * sizeof(double));
+    L.off_npart = o; o = al(o + (size_t)L.ntile * r.warps * nbt * r.kcp * sizeof(double));
     L.nta = (int)cdiv(N, GN_T); L.ntb = (int)cdiv((int64_t)nbt * r.kcp, GN_T);
     const int64_t nk = cdiv(p, GN_KC);
     int64_t ns = cdiv(4LL * num_sms(), (int64_t)L.nta * L.ntb);
@@ -415,24 +416,31 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     return L;
 }
 
-template <int NKS, int NBLK>
+template <int NKS, int NBLK, int W>
 static int launch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
-    rb_vs_kernel<NKS, NBLK><<<ntile, RD_THREADS, r.smem_bytes, st>>>(a);
+    PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
+    rb_vs_kernel<NKS, NBLK, W><<<ntile, W * 32, r.smem_bytes, st>>>(a);
     PLSB_LAUNCH_CHECK("rb_vs_kernel");
     return PLSB200_OK;
 }
 
 template <int NBLK>
 static int dispatch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
-    switch (r.nks) {
-#define PLSB_CASE(n) case n: return launch_vs<n, NBLK>(r, a, ntile, st);
-        PLSB_CASE(4) PLSB_CASE(8) PLSB_CASE(12) PLSB_CASE(16) PLSB_CASE(20) PLSB_CASE(24) PLSB_CASE(28) PLSB_CASE(32)
-        PLSB_CASE(36) PLSB_CASE(40) PLSB_CASE(44) PLSB_CASE(48) PLSB_CASE(52) PLSB_CASE(56) PLSB_CASE(60) PLSB_CASE(64)
-        PLSB_CASE(68) PLSB_CASE(72) PLSB_CASE(76) PLSB_CASE(80)
-        PLSB_CASE(84) PLSB_CASE(88) PLSB_CASE(92) PLSB_CASE(96)
+    if (r.warps == 16) {
+        switch (r.nks) {
+#define PLSB_CASE(n) case n: return launch_vs<n, NBLK, 16>(r, a, ntile, st);
+            PLSB_CASE(4) PLSB_CASE(8) PLSB_CASE(12) PLSB_CASE(16) PLSB_CASE(20) PLSB_CASE(24) PLSB_CASE(28) PLSB_CASE(32)
 #undef PLSB_CASE
-        default: break;
+            default: break;
+        }
+    } else {
+        switch (r.nks) {
+#define PLSB_CASE(n) case n: return launch_vs<n, NBLK, 8>(r, a, ntile, st);
+            PLSB_CASE(36) PLSB_CASE(40) PLSB_CASE(44) PLSB_CASE(48) PLSB_CASE(52) PLSB_CASE(56) PLSB_CASE(60) PLSB_CASE(64) PLSB_CASE(68) PLSB_CASE(72)
+            PLSB_CASE(76) PLSB_CASE(80) PLSB_CASE(84) PLSB_CASE(88) PLSB_CASE(92) PLSB_CASE(96)
+#undef PLSB_CASE
+            default: break;
+        }
     }
     set_err("rb_boot_dmma_f64: no kernel for %d k-steps x %d column blocks", r.nks, NBLK);
     return PLSB200_EUNSUPPORTED;
@@ -495,7 +503,7 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
         }
         if (rc != PLSB200_OK) return rc;
         rd_norm_reduce_kernel<<<(unsigned)cdiv((int64_t)nbt * a.kc * 32, 256), 256, 0, st>>>(
-            d_npart, L.ntile * RD_WARPS, nbt, r.kcp, a.kc, K, a.k0, nrm2 + (size_t)b0 * K);
+            d_npart, L.ntile * r.warps, nbt, r.kcp, a.kc, K, a.k0, nrm2 + (size_t)b0 * K);
         PLSB_LAUNCH_CHECK("rd_norm_reduce_kernel");
         if (want_t) {
             const size_t smem = (size_t)2 * GN_STAGES * GN_T * GN_STR * sizeof(double);
