@@ -78,6 +78,14 @@ int plsb200_xv_f64(const double* X, int N, int64_t p, int64_t ldx, const double*
 int plsb200_nspace_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
                        const double* Lmat, int Kt, double* d2, double* T, void* stream);
 
+/* ---- per-resample SVD mode ("rotate_method = 0" of the older plspy API: re-run the SVD for every permutation).
+ * With E = Lop^T (N x K: the rows of the cross-block builder, NOT projected on the original singular vectors)
+ *     B[r] = C_r^T G C_r  (K x K)  =  M_r M_r^T,  M_r = Lop . X[idx_r]  the resampled cross-block matrix,
+ * whose eigenvalues (plsb200_sym_eig_f64) are the squared singular values of M_r.  d2[r] = diag(B[r]).
+ * B: R x K x K.  Needs 2 N K doubles of shared memory in one chunk.                                          */
+int plsb200_nspace_gram_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
+                            double* d2, double* B, void* stream);
+
 /* ---- permutation counters -------------------------------------------------------------------------
  * s_hat = sqrt(d2) (set to 0 where |s_hat| < thresh when thresh > 0: bootstrap_permutation.py:436),
  * counts[k]     += (s_hat[r,k] >= s_ref[k])                              (:427/:433/:437)

@@ -43,6 +43,8 @@ SIGNATURES = {
                                c_size_t, c_void_p]),
     "plsb200_nspace_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p, c_int,
                                    c_double_p, c_double_p, c_void_p]),
+    "plsb200_nspace_gram_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p, c_double_p,
+                                        c_void_p]),
     "plsb200_perm_count_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_double, c_double_p,
                                        c_void_p, c_double_p, c_void_p]),
     "plsb200_uhat_f64": (c_int, [c_double_p, c_int64, c_int, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p,

@@ -310,8 +310,13 @@ class _ResampleTestPLS(ResampleTest):
 
     def __init__(self, X, Y, U, s, V, cond_order, mctype, contrast=None, preprocess=None, nperm=1000,
                  nboot=1000, bscan=None, Xbscan=None, Ybscan=None, lvcorrs_orig=None, Tvsc_orig=None,
-                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None, precision="fp64"):
+                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None, precision="fp64", rotate_method=2):
         self.CI = CI
+        if rotate_method not in (0, 1, 2):
+            raise ValueError("rotate_method must be 0 (SVD), 1 (Procrustes) or 2 (derived)")
+        if rotate_method == 0 and self.pls_alg != "mct":
+            raise exceptions.NotImplementedError("rotate_method=0 (per-permutation SVD) is provided for mct only")
+        self.rotate_method = rotate_method
         _log(f"PLS ALG: {self.pls_alg}")
         eng = engine if engine is not None else (
             Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
@@ -322,7 +327,8 @@ class _ResampleTestPLS(ResampleTest):
             # them after the bootstrap work has been enqueued too, so the GPU never idles between the two tests
             perm_pending = self._permutation_test(
                 X, Y, U, s, V, cond_order, mctype, nperm, self.pls_alg, preprocess=preprocess, contrast=contrast,
-                bscan=bscan, Xbscan=Xbscan, Ybscan=Ybscan, indices=perm_indices, engine=eng, _defer=True)
+                bscan=bscan, Xbscan=Xbscan, Ybscan=Ybscan, indices=perm_indices, engine=eng, _defer=True,
+                rotate_method=rotate_method)
         else:
             self.permute_ratio = "NA"
             self.stepdown_ratio = "NA"
@@ -349,9 +355,18 @@ class _ResampleTestPLS(ResampleTest):
     @staticmethod
     def _permutation_test(X, Y, U, s, V, cond_order, mctype, niter, pls_alg, preprocess=None, contrast=None,
                           threshold=1e-12, bscan=None, Xbscan=None, Ybscan=None, indices=None, engine=None,
-                          _defer=False):
+                          _defer=False, rotate_method=2):
         """bootstrap_permutation.py:265-464.  `s` is thresholded in place like the reference (:295).
-        `_defer=True` returns a function that waits for the device results and builds the outputs."""
+        `_defer=True` returns a function that waits for the device results and builds the outputs.
+
+        rotate_method (the option of the older plspy API that survives in docs/_build/html/plspy.html:438-440):
+          2 "derived" (the current reference code and the default): s_hat = column norms of permuted^T U;
+          1 "Procrustes": [pu, ps, pv] = svd(permuted), rotation Q = v u^T from svd(U^T pv), s_hat = column norms
+            of pv ps Q.  U and pv are square orthogonal K x K matrices, so Q = pv^T U exactly and
+            s_hat_k^2 = U_k^T (pv ps^2 pv^T) U_k = || permuted^T U_k ||^2: identical to the derived value, and served
+            by the same kernels (tests/test_gpu_kernels.py checks this against an explicit numpy Procrustes);
+          0 "SVD": s_hat = the singular values of the permuted cross-block matrix itself (mct only): K x K Gram matrix
+            through G (plsb200_nspace_gram_f64) + one-warp-per-matrix Jacobi eigensolver (plsb200_sym_eig_f64)."""
         eng = engine if engine is not None else Engine(X)
         s[np.abs(s) < threshold] = 0
         if pls_alg in ("mb", "cmb"):
@@ -381,7 +396,14 @@ class _ResampleTestPLS(ResampleTest):
         else:
             Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
             K = E.shape[1]
-            d2, _ = eng.nspace(E, idx_dev)
+            if rotate_method == 0:
+                # squared singular values of M_r = Lop X[idx_r]: eigenvalues of M_r M_r^T = C_r^T G C_r
+                Bfull = eng.nspace_gram(np.ascontiguousarray(Lop.T), idx_dev)
+                d2, _ = eng.sym_eig(Bfull)
+                d2 = torch.clamp(d2, min=0.0)
+                K = d2.shape[1]
+            else:
+                d2, _ = eng.nspace(E, idx_dev)
         counts, s_hat = eng.perm_count(d2, s, totcov_org, threshold if pls_alg in ("mct", "rb") else 0.0)
         dist.allreduce_sum_(counts)
         s_hat = dist.gather_rows(s_hat, niter, lo)

@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(512) nspace_kernel(const double* __restrict__ 
                                                       long long e_stride, int K, int ldk, int koff,
                                                       const int32_t* __restrict__ idx,
                                                       const double* __restrict__ Lmat, int Kt,
-                                                      double* __restrict__ d2, double* __restrict__ T) {
+                                                      double* __restrict__ d2, double* __restrict__ T,
+                                                      double* __restrict__ Bfull) {
     extern __shared__ __align__(16) double sm[];
     double* Es = sm;                      // [N][K]
     double* Hs = Es + (size_t)N * K;      // [N][K]
@@ -70,6 +71,16 @@ __global__ void __launch_bounds__(512) nspace_kernel(const double* __restrict__ 
         if (lane == 0) {
             d2[(size_t)r * ldk + koff + k] = s;
             dn[k] = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+        }
+    }
+    // optional: the whole K x K matrix B = C^T G C = C^T H (the Gram matrix of the resampled cross-block matrix when
+    // E carries the builder's rows instead of projected weights): input of the per-resample SVD mode
+    if (Bfull != nullptr) {
+        for (int o = tid; o < K * K; o += nt) {
+            const int k1 = o / K, k2 = o % K;
+            double s = 0.0;
+            for (int i = 0; i < N; ++i) s = fma(Es[i * K + k1], Hs[ids[i] * K + k2], s);
+            Bfull[(size_t)r * K * K + o] = s;
         }
     }
     if (T == nullptr) return;
@@ -180,13 +191,13 @@ __global__ void __launch_bounds__(CS_COLS * CS_ROWS) colstd_kernel(const double*
 template <int KT>
 static int launch_nspace(const double* G, int N, const double* E, long long e_stride, int K, int ldk, int koff,
                          const int32_t* idx, int R,
-                         const double* Lmat, int Kt, double* d2, double* T, cudaStream_t st) {
+                         const double* Lmat, int Kt, double* d2, double* T, double* Bfull, cudaStream_t st) {
     size_t smem = ((size_t)2 * N * K + K) * sizeof(double) + (size_t)N * sizeof(int);
     PLSB_CUDA(cudaFuncSetAttribute(nspace_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = (int)cdiv(N, 32) * 32;
     if (threads > 512) threads = 512;
     if (threads < 128) threads = 128;
-    nspace_kernel<KT><<<R, threads, smem, st>>>(G, N, E, e_stride, K, ldk, koff, idx, Lmat, Kt, d2, T);
+    nspace_kernel<KT><<<R, threads, smem, st>>>(G, N, E, e_stride, K, ldk, koff, idx, Lmat, Kt, d2, T, Bfull);
     PLSB_LAUNCH_CHECK("nspace_kernel");
     return PLSB200_OK;
 }
@@ -196,7 +207,8 @@ static int launch_nspace(const double* G, int N, const double* E, long long e_st
 using namespace plsb;
 
 static int nspace_dispatch(const double* G, int N, const double* E, long long e_stride, int K, const int32_t* idx,
-                           int R, const double* Lmat, int Kt, double* d2, double* T, cudaStream_t st) {
+                           int R, const double* Lmat, int Kt, double* d2, double* T, cudaStream_t st,
+                           double* Bfull = nullptr) {
     // columns are independent: chunk K so that E and H chunks (2 * N * Kc doubles) fit in shared memory
     const size_t budget = 200 * 1024;
     int kc = K;
@@ -205,14 +217,18 @@ static int nspace_dispatch(const double* G, int N, const double* E, long long e_
         set_err("nspace_f64: N=%d too large for shared memory", N);
         return PLSB200_EUNSUPPORTED;
     }
+    if (Bfull != nullptr && kc < K) {
+        set_err("nspace_gram_f64: N=%d x K=%d does not fit in shared memory in one column chunk", N, K);
+        return PLSB200_EUNSUPPORTED;
+    }
     for (int k0 = 0; k0 < K; k0 += kc) {
         const int kw = K - k0 < kc ? K - k0 : kc;
         int rc;
-        if (kw <= 4) rc = launch_nspace<4>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 8) rc = launch_nspace<8>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 12) rc = launch_nspace<12>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else if (kw <= 16) rc = launch_nspace<16>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
-        else rc = launch_nspace<24>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, st);
+        if (kw <= 4) rc = launch_nspace<4>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, Bfull, st);
+        else if (kw <= 8) rc = launch_nspace<8>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, Bfull, st);
+        else if (kw <= 12) rc = launch_nspace<12>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, Bfull, st);
+        else if (kw <= 16) rc = launch_nspace<16>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, Bfull, st);
+        else rc = launch_nspace<24>(G, N, E, e_stride, kw, K, k0, idx, R, Lmat, Kt, d2, T, Bfull, st);
         if (rc != PLSB200_OK) return rc;
     }
     return PLSB200_OK;
@@ -225,6 +241,14 @@ extern "C" int plsb200_nspace_f64(const double* G, int N, const double* E, int K
     PLSB_CHECK_ARG((T == nullptr) || (Lmat != nullptr && Kt > 0), "nspace_f64: T requested without Lmat");
     if (R == 0) return PLSB200_OK;
     return nspace_dispatch(G, N, E, 0, K, idx, R, Lmat, Kt, d2, T, (cudaStream_t)stream);
+}
+
+extern "C" int plsb200_nspace_gram_f64(const double* G, int N, const double* E, int K, const int32_t* idx, int R,
+                                       double* d2, double* B, void* stream) {
+    PLSB_CHECK_ARG(G && E && idx && d2 && B, "nspace_gram_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "nspace_gram_f64: bad shape N=%d K=%d R=%d", N, K, R);
+    if (R == 0) return PLSB200_OK;
+    return nspace_dispatch(G, N, E, 0, K, idx, R, nullptr, 0, d2, nullptr, (cudaStream_t)stream, B);
 }
 
 extern "C" int plsb200_nspace_coef_f64(const double* G, int N, const double* C, int K, int R, const double* Lmat,

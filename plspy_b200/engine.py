@@ -176,6 +176,17 @@ class Engine:
                                          self._p(d2), self._p(T), self._stream()), "nspace_f64")
         return d2, T
 
+    def nspace_gram(self, E, idx):
+        """B[r] = C_r^T G C_r (R x K x K), C_r = scatter(E, idx_r): Gram matrix of the resampled cross-block matrix."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        d2 = self._empty(R, K); B = self._empty(R, K, K)
+        G = self.G
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_nspace_gram_f64(self._p(G), self.N, self._p(E), K, self._p(idx), R, self._p(d2),
+                                              self._p(B), self._stream()), "nspace_gram_f64")
+        return B
+
     def perm_count(self, d2, s_ref, totcov_ref, thresh, counts=None, mb_total=None):
         d2 = self.to_device(d2, F64)
         R, K = int(d2.shape[0]), int(d2.shape[1])

@@ -18,7 +18,9 @@ def PLS(*args, **kwargs):
     Drop-in for `plspy.PLS`: same arguments, same result attributes; the permutation, bootstrap and
     split-half loops run on a B200 through libplsb200.  Extra optional keywords: `perm_indices`,
     `boot_indices` (pre-generated resampling index matrices), `engine` (an `Engine` already holding X),
-    `precision` ("fp64" = exact mode, default; "tf32x3" = fast mode for the bootstrap moment GEMM).
+    `precision` ("fp64" = exact mode, default; "tf32x3" = fast mode for the bootstrap moment GEMM),
+    `rotate_method` (2 = derived, the reference's behaviour and the default; 1 = Procrustes; 0 = per-permutation SVD,
+    mct only -- see `_ResampleTestPLS._permutation_test`).
     """
     pls_method = kwargs.pop("pls_method", "mct")
     kwargs["pls_alg"] = pls_method

@@ -44,7 +44,7 @@ class PLSBase(abc.ABC):
         return cls._subclasses[pls_method](*args, **kwargs)
 
     # ---- shared helpers -------------------------------------------------------------------
-    _ENGINE_KWARGS = ("perm_indices", "boot_indices", "engine", "device", "precision")
+    _ENGINE_KWARGS = ("perm_indices", "boot_indices", "engine", "device", "precision", "rotate_method")
 
     def _take_kwargs(self, kwargs):
         self.pls_alg = kwargs["pls_alg"]
@@ -129,7 +129,8 @@ class PLSBase(abc.ABC):
             nperm=self.num_perm, nboot=self.num_boot, CI=self.CI,
             perm_indices=self._engine_kwargs.get("perm_indices"),
             boot_indices=self._engine_kwargs.get("boot_indices"),
-            engine=self._engine_kwargs.get("engine"), precision=self._engine_kwargs.get("precision", "fp64"), **kw)
+            engine=self._engine_kwargs.get("engine"), precision=self._engine_kwargs.get("precision", "fp64"),
+            rotate_method=self._engine_kwargs.get("rotate_method", 2), **kw)
 
     def _split_half(self, Y, mctype, contrasts, **kw):
         """pls_classes.py:285-318 (identical block in every class)."""

@@ -295,3 +295,43 @@ def test_rb_boot_dmma_matches_fma_kernel_and_numpy(torch_cuda, cells, unit, p, K
     _, _, T0, n0 = eng.rb_boot(eng.X, Qd, Wd, cs, unit_cells=unit, want_t=False)
     assert T0 is None
     np.testing.assert_allclose(n0.cpu().numpy(), ref[3], rtol=1e-9)
+
+
+def test_rotate_methods_svd_and_procrustes_against_numpy(torch_cuda):
+    """Per-permutation SVD mode (rotate_method=0) and Procrustes mode (1) of the older plspy API: no code for them
+    exists in the reference tree, so the oracle is plain numpy on the permuted cross-block matrix
+    (np.linalg.svd; Procrustes rotation as in the MATLAB PLS toolbox: Q = v u^T from svd(U^T pv))."""
+    import plspy_b200
+    from plspy_b200 import class_functions as cf
+    rs = np.random.RandomState(8)
+    groups, C, p, P = (7, 9), 3, 800, 60
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)); X[:7, :60] += 1.0
+    co = np.array([[n] * C for n in groups])
+    out = {}
+    for rm in (0, 1, 2):
+        np.random.seed(21)
+        out[rm] = plspy_b200.PLS(X.copy(), groups, C, num_perm=P, num_boot=0, mctype=2, pls_method="mct",
+                                 rotate_method=rm)
+    idx = out[0].resample_tests.perm_debug_dict["indices"]
+    A = cf._centring_operator(co, 2)
+    U, s, _ = cf._run_pls(A @ X)
+    s_thr = s.copy(); s_thr[np.abs(s_thr) < 1e-12] = 0
+    live = s_thr > 1e-8 * s_thr.max()
+    sv = np.empty((P, len(s))); proc = np.empty((P, len(s)))
+    for r in range(P):
+        M = A @ X[idx[r]]
+        pu, ps, pvt = np.linalg.svd(M, full_matrices=False)
+        sv[r] = ps
+        u_, _, vt_ = np.linalg.svd(U.T @ pu)           # design-side saliences: K x K, square orthogonal
+        Q = (u_ @ vt_).T                               # rotation that best aligns pu with U
+        proc[r] = np.linalg.norm((pu * ps) @ Q, axis=0)
+    rt0 = out[0].resample_tests
+    np.testing.assert_allclose(rt0.perm_debug_dict["s_list"][:, live], sv[:, live], rtol=1e-9)
+    np.testing.assert_array_equal(rt0.permute_ratio[live], ((sv >= s_thr).sum(0) / (P + 1))[live])
+    # Procrustes == derived (square orthogonal saliences), both equal the explicit numpy Procrustes
+    np.testing.assert_array_equal(out[1].resample_tests.permute_ratio, out[2].resample_tests.permute_ratio)
+    np.testing.assert_allclose(out[1].resample_tests.perm_debug_dict["s_list"][:, live], proc[:, live], rtol=1e-8)
+    with pytest.raises(Exception):
+        plspy_b200.PLS(X.copy(), groups, C, num_perm=3, num_boot=0, pls_method="cst",
+                       contrasts=np.linalg.qr(rs.standard_normal((6, 2)))[0], rotate_method=0)
