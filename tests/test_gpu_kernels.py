@@ -335,3 +335,29 @@ def test_rotate_methods_svd_and_procrustes_against_numpy(torch_cuda):
     with pytest.raises(Exception):
         plspy_b200.PLS(X.copy(), groups, C, num_perm=3, num_boot=0, pls_method="cst",
                        contrasts=np.linalg.qr(rs.standard_normal((6, 2)))[0], rotate_method=0)
+
+
+def test_rb_boot_dmma_chunked_launches_accumulate(torch_cuda):
+    """several launches over bootstrap chunks (small workspace) accumulate the same moments as one launch, and a
+    design with more than 16 blocks falls back to the general kernel"""
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(4)
+    cells = [10] * 4
+    cs = np.concatenate(([0], np.cumsum(cells))).astype(np.int32)
+    N, p, K, R = 40, 900, 12, 23
+    Xc = rs.standard_normal((N, p)); Q = rs.standard_normal((R, N, K)); W = np.full((R, N), 0.1)
+    eng = Engine(Xc)
+    Qd = eng.to_device(Q, torch_cuda.float64); Wd = eng.to_device(W, torch_cuda.float64)
+    one = eng.rb_boot(eng.X, Qd, Wd, cs)
+    from plspy_b200._lib import lib
+    per_boot = lib.plsb200_rb_boot_dmma_f64_workspace(N, p, K, 1, cs.ctypes.data, 4, 0, 1)
+    many = eng.rb_boot(eng.X, Qd, Wd, cs, max_ws_bytes=5 * per_boot)      # 5 bootstraps per launch -> 5 launches
+    for a_, b_ in zip(one, many):
+        np.testing.assert_allclose(b_.cpu().numpy(), a_.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    cells = [3] * 17                                                       # 17 blocks: beyond the DMMA path
+    cs = np.concatenate(([0], np.cumsum(cells))).astype(np.int32)
+    assert lib.plsb200_rb_boot_dmma_f64_workspace(51, 100, 4, 1, cs.ctypes.data, 17, 0, 1) == 0
+    X2 = rs.standard_normal((51, 100)); Q2 = rs.standard_normal((2, 51, 4)); W2 = np.full((2, 51), 1 / 3)
+    e2 = Engine(X2)
+    s1, s2, T, n2 = e2.rb_boot(e2.X, e2.to_device(Q2, torch_cuda.float64), e2.to_device(W2, torch_cuda.float64), cs)
+    assert np.isfinite(T.cpu().numpy()).all() and (n2.cpu().numpy() > 0).all()

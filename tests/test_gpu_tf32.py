@@ -109,3 +109,18 @@ def test_fast_mode_against_reference_goldens(case):
     np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-4)
     np.testing.assert_allclose(rt.boot_ratios[:, live], g["boot_ratios"][:, live], rtol=1e-4)
     np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("N,p,K,R", [(8, 5, 24, 1), (300, 128, 12, 20), (300, 129, 12, 21), (16, 4000, 2, 1000)])
+def test_boot_moments_tf32_corner_shapes(N, p, K, R):
+    """fewer voxels than one tile, exactly one tile, one voxel into the second tile, a single resample, many tiny
+    resamples (128 per column tile)"""
+    from plspy_b200.engine import Engine
+    X, E, idx = _mk(N, p, K, R, 5 + N + p)
+    eng = Engine(X, precision="tf32x3")
+    VS = np.stack([X.T @ _scatter(E, idx[r]) for r in range(R)])
+    s1, s2 = eng.boot_moments(E, idx)
+    colscale = np.sqrt((X ** 2).sum(0))[:, None] * np.sqrt((E ** 2).sum(0))[None, :] + 1e-30
+    assert (np.abs(s1.cpu().numpy() - VS.sum(0)) / (R * colscale)).max() < 1e-5
+    ref2 = (VS ** 2).sum(0)
+    np.testing.assert_allclose(s2.cpu().numpy(), ref2, rtol=3e-5, atol=1e-5 * ref2.max())
