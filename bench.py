@@ -59,10 +59,9 @@ def workload_name(groups, C, p, nperm, nboot):
 class ClockSampler:
     """SM clock, power and clock-event reasons of one GPU through NVML (nvidia_ml_py), sampled from the MAIN thread
     once per step at the moment the dominant kernel has just been launched (the engine's `on_mark` hook), i.e.
-    while the GPU is under load and the host has nothing else to do.  Polling from a second thread or from an
-    external `nvidia-smi -lms` process measurably disturbed the timed region (isolated steps stalled by 20-130 ms
-    when a query coincided with the step's own driver calls), so neither is used; nvidia-smi remains the fallback
-    when NVML cannot be loaded and is then started well before the timed region."""
+    while the GPU is under load and the host has nothing else to do.  Polling every 20 ms from a second thread
+    slowed every step by 10-15 %, so no thread and no external `nvidia-smi -lms` process is used; nvidia-smi remains
+    the fallback when NVML cannot be loaded and is then started well before the timed region."""
 
     NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
              ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
@@ -70,7 +69,7 @@ class ClockSampler:
              ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
 
     def __init__(self, gpu_index):
-        self.rows, self._on, self._n = [], False, 0
+        self.rows, self._on, self._n, self.armed = [], False, 0, False
         self.nv = self.h = self.proc = self.path = None
         self.gpu_index = gpu_index
         try:
@@ -110,7 +109,8 @@ class ClockSampler:
             pass
 
     def on_mark(self, name):
-        """Engine hook: called before and after the launch of a marked kernel; sample after the launch."""
+        """Engine hook: called before and after the launch of a marked kernel; one reading per step, taken right
+        after the dominant kernel has been launched (the GPU is under load, the host has nothing else to do)."""
         if name == "boot_moments":
             self._n += 1
             if self._n % 2 == 0:
@@ -131,7 +131,7 @@ class ClockSampler:
             self.proc = None
             return out
         out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [],
-               "source": "nvml, main thread, one sample per step while the dominant kernel runs"}
+               "source": "nvml, main thread, one reading per step while the dominant kernel runs"}
         rows = list(self.rows)
         if rows:
             out["sm_mhz"] = statistics.median(r[0] for r in rows)
@@ -329,10 +329,14 @@ def run_gpu(args):
     def measure(precision):
         """value arm (inputs resident in HBM) and e2e arm (pinned host buffers in, host results out) for one
         precision mode; returns a dict of raw timings."""
-        for _ in range(args.warmup):
-            one_pass(Xd, Vd, gpd, gbd, precision=precision)
-        events = {}
+        # warm-up with the same object-retention pattern as the timed loop (the previous engine stays alive until
+        # the next pass has finished), so that torch's caching allocators reach their steady state -- two sets
+        # of blocks -- before the timed region; otherwise the second timed step pays a one-off 10-50 ms for
+        # fresh device / pinned allocations
         keep = {}
+        for _ in range(max(args.warmup, 3)):
+            keep["eng"] = one_pass(Xd, Vd, gpd, gbd, {}, precision)[0]
+        events = {}
         launches0 = _lib.launch_count()
         if sampler is not None:
             sampler.begin()
