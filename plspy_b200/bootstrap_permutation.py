@@ -463,18 +463,21 @@ class _ResampleTestPLS(ResampleTest):
             left = eng.uhat(XL, Lop, idx_dev)                               # U_hat (:617, :631)
         else:
             left = None
+        # the per-bootstrap N-space outputs are complete here: assemble them across ranks and start their
+        # device -> host copies on a second stream, so that they overlap the moment GEMM enqueued next
+        Tdist = dist.gather_rows(Tdist, niter, lo)
+        if left is not None:
+            left = dist.gather_rows(left, niter, lo)
+        fetch_small = eng.to_host_async(eng.colstd(Tdist), Tdist, left, side=True)
         if hi > lo:
             s1, s2 = eng.boot_moments(E, idx_dev, pivot=numer)              # K4
         else:
             s1 = torch.zeros_like(numer); s2 = torch.zeros_like(numer)
         dist.allreduce_packed_([s1, s2])
         std_errs, boot_ratios = eng.boot_finalize(s1, s2, niter, numer=numer)   # (:695-703)
-        Tdist = dist.gather_rows(Tdist, niter, lo)
-        if left is not None:
-            left = dist.gather_rows(left, niter, lo)
         z = norm.ppf(1 - (1 - CI) / 2)                                      # (:709)
-        std_T, std_errs_h, boot_ratios_h, Tdist_h, left_h = eng.to_host(
-            eng.colstd(Tdist), std_errs, boot_ratios, Tdist, left)
+        std_errs_h, boot_ratios_h = eng.to_host(std_errs, boot_ratios)
+        std_T, Tdist_h, left_h = fetch_small()
         half = std_T * z                                                    # (:715-716)
         conf_int = (Tvsc_orig - half, Tvsc_orig + half)
 

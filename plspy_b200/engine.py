@@ -68,20 +68,31 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def to_host_async(self, *tensors):
+    def to_host_async(self, *tensors, side=False):
         """Enqueue device -> host copies into pinned staging buffers (torch's caching host allocator) and return
         a function that waits for them (one event synchronisation) and hands back numpy arrays; None passes
-        through.  Lets the caller keep enqueuing GPU work before it blocks."""
+        through.  Lets the caller keep enqueuing GPU work before it blocks.  `side=True` issues the copies on a
+        second stream (after everything enqueued so far), so that they overlap the kernels enqueued next."""
+        cur = torch.cuda.current_stream(self.device)
+        stream = cur
+        if side:
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            stream = self._copy_stream
+            stream.wait_stream(cur)
         staged = []
-        for t in tensors:
-            if t is None:
-                staged.append(None)
-                continue
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            staged.append(h)
+        with torch.cuda.stream(stream):
+            for t in tensors:
+                if t is None:
+                    staged.append(None)
+                    continue
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                if side:
+                    t.record_stream(stream)
+                staged.append(h)
         done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(self.device))
+        done.record(stream)
 
         def wait():
             done.synchronize()
