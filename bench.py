@@ -361,7 +361,8 @@ def run_gpu(args):
                 "launches": launches, "clocks": clocks, "e2e_ms": e2e_ms, "rt": last["rt"]}
 
     units_step = (nperm + nboot) * world
-    h2d = Xh.numel() * 8 + Vh.numel() * 8 + idx_p.nbytes + idx_b.nbytes
+    # per rank: its 1/world share of the replicated X (the rest arrives over NVLink), V and its index shards
+    h2d = -(-N // world) * p * 8 + Vh.numel() * 8 + idx_p.nbytes + idx_b.nbytes
     main = measure(args.precision)
     fast = measure("tf32x3") if (args.precision == "fp64" and not args.no_fast_mode) else None
     ms_step, kern_ms, launches, clocks, e2e_ms, rt = (main[k] for k in ("ms_step", "kern_ms", "launches", "clocks",
