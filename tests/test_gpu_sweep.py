@@ -1,0 +1,83 @@
+"""Randomised (seeded) sweep of small designs through the whole public path against the oracle: every method, random
+group counts / sizes, condition counts, voxel counts, behaviour counts, mean-centring types and bscan subsets.
+Both sides draw their resampling indices from the global numpy stream after the same seed (the product through the
+native generator), so index generation, kernels and host glue are all exercised.  Tolerances as in
+test_gpu_parity.py: p-values exact, floating-point results 1e-8 relative on live latent variables for the task
+methods.  Behaviour / multiblock bootstraps are held to 1e-6: the kernels form the per-voxel block variance of a
+resample in one pass (sum w x^2 - (sum w x)^2 on block-centred data) where the reference z-scores in two passes,
+so a resample that happens to draw almost identical rows for a block (variance ~1e-9 of the second moment; seed
+122 has one such voxel) loses digits there -- 7e-8 on that voxel's std_errs, far inside the 1e-4 of the north star."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _design(seed):
+    rs = np.random.RandomState(seed)
+    method = ["mct", "cst", "rb", "csb", "mb", "cmb"][seed % 6]
+    G = int(rs.randint(1, 4))
+    C = int(rs.randint(2, 5))
+    groups = tuple(int(n) for n in rs.randint(4, 9, size=G))
+    p = int(rs.choice([37, 130, 300, 515, 1030]))
+    nb = int(rs.randint(1, 4))
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)) + float(rs.choice([0.0, 5.0]))
+    row = 0
+    for gsz in groups:
+        for c in range(C):
+            X[row:row + gsz, : max(2, p // 10)] += 0.7 * rs.standard_normal(max(2, p // 10))
+            row += gsz
+    kw = {}
+    if method in ("rb", "csb", "mb", "cmb"):
+        kw["Y"] = rs.standard_normal((N, nb)) + 0.4 * X[:, :nb]
+    if method in ("mct", "cst", "mb", "cmb"):
+        kw["mctype"] = int(rs.randint(0, 4)) if G > 1 else int(rs.choice([0, 2]))
+    if method in ("mb", "cmb"):
+        nbs = int(rs.randint(1, C + 1))
+        kw["bscan"] = sorted(int(b) for b in rs.choice(C, size=nbs, replace=False))
+    if method == "cst":
+        kw["contrasts"] = np.linalg.qr(rs.standard_normal((G * C, min(3, G * C - 1))))[0]
+    elif method == "csb":
+        K = G * C * nb
+        kw["contrasts"] = np.linalg.qr(rs.standard_normal((K, K)))[0]      # square: the reference's CI step needs L == K'
+    elif method == "cmb":
+        K = G * (C + len(kw["bscan"]) * nb)
+        kw["contrasts"] = np.linalg.qr(rs.standard_normal((K, min(3, K - 1))))[0]
+    return method, X, groups, C, kw
+
+
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_random_design_matches_oracle(seed):
+    import plspy_b200
+    method, X, groups, C, kw = _design(seed)
+    P = B = 25
+    okw = dict(Y=kw.get("Y"), contrasts=kw.get("contrasts"), mctype=kw.get("mctype", 0), bscan=kw.get("bscan"))
+    np.random.seed(seed)
+    try:
+        o = oracle.run_full(method, X.copy(), groups, C, nperm=P, nboot=B, **{k: (v.copy() if hasattr(v, "copy") else v)
+                                                                                 for k, v in okw.items() if v is not None})
+    except Exception as e:      # designs the reference algorithm itself rejects are not parity cases
+        pytest.skip(f"oracle rejects this design: {e}")
+    np.random.seed(seed)
+    res = plspy_b200.PLS(X.copy(), groups, C, num_perm=P, num_boot=B, pls_method=method,
+                         **{k: (v.copy() if hasattr(v, "copy") else v) for k, v in kw.items()})
+    rt = res.resample_tests
+    s = np.asarray(o["s"])
+    live = np.abs(s) > 1e-8 * np.abs(s).max()
+    np.testing.assert_allclose(res.s[live], s[live], rtol=1e-9)
+    np.testing.assert_array_equal(rt.permute_ratio[live], np.asarray(o["perm"]["permute_ratio"])[live])
+    np.testing.assert_array_equal(rt.stepdown_ratio[live], np.asarray(o["perm"]["stepdown_ratio"])[live])
+    tol = 1e-8 if method in ("mct", "cst") else 1e-6
+    np.testing.assert_allclose(rt.std_errs[:, live], o["boot"]["std_errs"][:, live], rtol=tol, atol=1e-12)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=tol, atol=1e-10)
+    lo_ref = o["boot"]["conf_ints"][0]
+    np.testing.assert_allclose(rt.conf_ints[0][:, live], lo_ref[:, live], rtol=1e-7, atol=1e-9)
+    # after the call both sides have consumed the same amount of the global stream
+    a = np.random.random(3)
+    np.random.seed(seed)
+    oracle.run_full(method, X.copy(), groups, C, nperm=P, nboot=B, **{k: (v.copy() if hasattr(v, "copy") else v)
+                                                                       for k, v in okw.items() if v is not None})
+    np.testing.assert_array_equal(a, np.random.random(3))
