@@ -44,7 +44,7 @@ def _design(seed):
         K = G * C * nb
         kw["contrasts"] = np.linalg.qr(rs.standard_normal((K, K)))[0]      # square: the reference's CI step needs L == K'
     elif method == "cmb":
-        K = G * (C + len(kw["bscan"]) * nb)
+        K = G * (C + C * nb)       # contrasts are given for the full design and masked by bscan (pls_classes.py:1788-1803)
         kw["contrasts"] = np.linalg.qr(rs.standard_normal((K, min(3, K - 1))))[0]
     return method, X, groups, C, kw
 
