@@ -50,6 +50,10 @@ const char* plsb200_last_error(void);
 /* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
 int64_t plsb200_launch_count(void);
 
+/* strided host -> device copy (cudaMemcpy2DAsync): uploads a voxel range (column block) of a pinned row-major X */
+int plsb200_copy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
+                       size_t height, void* stream);
+
 /* ---- K1: Gram matrix G = X . X^T (N x N), FP64 DMMA, split over voxel chunks, deterministic --------
  * Replaces the N x p work that every resample redoes in the reference (row gather + means + projection,
  * resample.py:79,153 + class_functions.py:7-95 + bootstrap_permutation.py:404): once G is known every

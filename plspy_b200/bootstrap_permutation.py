@@ -322,6 +322,22 @@ class _ResampleTestPLS(ResampleTest):
             Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
         perm_pending = None
+        early = None
+        if (eng is not None and eng.upload_in_flight and nboot > 0 and self.pls_alg in ("mct", "cst")
+                and dist.world()[1] == 1):
+            # X is still crossing PCIe in voxel ranges (Engine._upload_pipelined): the bootstrap moment GEMM is the
+            # one kernel that can start on the ranges already there, so it is enqueued before the permutation test,
+            # whose Gram matrix needs all of X.  Index matrices are drawn first, in the reference's order.
+            if nperm > 0:
+                s[np.abs(s) < 1e-12] = 0                       # as _permutation_test does before anything reads s
+                if perm_indices is None:
+                    perm_indices = resample.permutation_indices(self.pls_alg, nperm, cond_order, Y=Y, bscan=bscan,
+                                                                Ybscan=Ybscan)
+            if boot_indices is None:
+                boot_indices = resample.bootstrap_indices(self.pls_alg, nboot, cond_order, Y=Y, bscan=bscan,
+                                                          Ybscan=Ybscan)
+            early = self._bootstrap_moments_early(eng, U, s, V, cond_order, mctype, nboot, self.pls_alg, contrast,
+                                                  boot_indices)
         if nperm > 0:
             # the permutation kernels and their device->host copies are enqueued here; the host only waits for
             # them after the bootstrap work has been enqueued too, so the GPU never idles between the two tests
@@ -336,7 +352,7 @@ class _ResampleTestPLS(ResampleTest):
             out = self._bootstrap_test(
                 X, Y, U, s, V, cond_order, mctype, nboot, self.pls_alg, preprocess=preprocess, contrast=contrast,
                 bscan=bscan, Xbscan=Xbscan, Ybscan=Ybscan, lvcorrs_orig=lvcorrs_orig, Tvsc_orig=Tvsc_orig, CI=CI,
-                indices=boot_indices, engine=eng)
+                indices=boot_indices, engine=eng, _early=early)
             if self.pls_alg in ("rb", "csb"):
                 self.conf_ints, self.std_errs, self.boot_ratios, self.LVcorr, self.boot_debug_dict = out
             elif self.pls_alg in ("mb", "cmb"):
@@ -435,8 +451,9 @@ class _ResampleTestPLS(ResampleTest):
     @staticmethod
     def _bootstrap_test(X, Y, U, s, V, cond_order, mctype, niter, pls_alg, preprocess=None, dist_=(0.05, 0.95),
                         contrast=None, bscan=None, Xbscan=None, Ybscan=None, lvcorrs_orig=None, Tvsc_orig=None,
-                        CI=0.95, indices=None, engine=None):
-        """bootstrap_permutation.py:466-766 for the task methods (mct, cst)."""
+                        CI=0.95, indices=None, engine=None, _early=None):
+        """bootstrap_permutation.py:466-766 for the task methods (mct, cst).  `_early`: moments already enqueued by
+        `_bootstrap_moments_early` (pipelined upload of X)."""
         eng = engine if engine is not None else Engine(X)
         if indices is None:
             indices = resample.bootstrap_indices(pls_alg, niter, cond_order, Y=Y, bscan=bscan, Ybscan=Ybscan)
@@ -469,7 +486,9 @@ class _ResampleTestPLS(ResampleTest):
         if left is not None:
             left = dist.gather_rows(left, niter, lo)
         fetch_small = eng.to_host_async(eng.colstd(Tdist), Tdist, left, side=True)
-        if hi > lo:
+        if _early is not None:
+            s1, s2 = _early
+        elif hi > lo:
             s1, s2 = eng.boot_moments(E, idx_dev, pivot=numer)              # K4
         else:
             s1 = torch.zeros_like(numer); s2 = torch.zeros_like(numer)
@@ -495,6 +514,18 @@ class _ResampleTestPLS(ResampleTest):
             return eng.salience(E, _index_shard(eng, indices, niter, 0, niter)).cpu().numpy()
         debug.set_lazy("right_sv_sampled", _right)
         return conf_int, std_errs_h, boot_ratios_h, debug
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _bootstrap_moments_early(eng, U, s, V, cond_order, mctype, niter, pls_alg, contrast, indices):
+        """The moment GEMM of `_bootstrap_test` for the task methods, on its own (single process)."""
+        if isinstance(indices, tuple):
+            indices = indices[0]
+        _, _, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)
+        Vd = eng.to_device(V, torch.float64)
+        numer = Vd * eng.to_device(np.asarray(s, dtype=float), torch.float64) if contrast is None else Vd
+        idx_dev = _index_shard(eng, indices, niter, 0, niter)
+        return eng.boot_moments(E, idx_dev, pivot=numer)
 
     # ------------------------------------------------------------------------------------------
     @staticmethod

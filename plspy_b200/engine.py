@@ -41,17 +41,78 @@ class Engine:
         self.precision = precision
         self._ximage = None
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.X = self._upload_x(X)
-        if self.X.dim() != 2:
+        self._pending = None          # [(v0, v1, event)]: voxel ranges of X still being uploaded (see _upload_x)
+        self._X = self._upload_x(X)
+        if self._X.dim() != 2:
             raise ValueError("X must be 2-dimensional")
-        self.N, self.p = int(self.X.shape[0]), int(self.X.shape[1])
-        self.ldx = int(self.X.stride(0))
+        self.N, self.p = int(self._X.shape[0]), int(self._X.shape[1])
+        self.ldx = int(self._X.stride(0))
         self._G = None
         self.kernel_events = None     # set to {} to record CUDA events around named kernels (bench.py)
         self.on_mark = None           # optional callable(name) invoked at every _mark (bench.py: clock sampling)
-        self.h2d_bytes = 0 if (torch.is_tensor(X) and X.is_cuda) else self.X.numel() * 8
+        self.h2d_bytes = 0 if (torch.is_tensor(X) and X.is_cuda) else self._X.numel() * 8
 
     # ------------------------------------------------------------------ plumbing
+    PIPELINED_UPLOAD_MIN_BYTES = 64 << 20
+    UPLOAD_CHUNKS = 4
+
+    @property
+    def X(self):
+        """The device copy of X.  If a pipelined upload is still in flight the current stream is made to wait for
+        all of it first (kernels that can start on the voxel ranges already uploaded use `_x_ranges` instead)."""
+        if self._pending is not None:
+            self._start_upload()
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._pending[-1][2])       # the copy stream is in order: the last event covers all
+            self._pending = None
+        return self._X
+
+    def _x_ranges(self):
+        """Voxel ranges of X with the event after which each is on the device ([(0, p, None)] when X is resident)."""
+        if self._pending is None:
+            return [(0, self.p, None)]
+        self._start_upload()
+        return list(self._pending)
+
+    @property
+    def upload_in_flight(self):
+        return self._pending is not None
+
+    def _upload_pipelined(self, Xh):
+        """Pinned host X -> device in UPLOAD_CHUNKS voxel ranges on a copy stream, one event per range, so that the
+        voxel-tiled kernels (Gram partials, TF32 split, bootstrap moment GEMM) can start on the first range while
+        the rest is still crossing PCIe.  The copies are only enqueued at the first use of X (`_start_upload`):
+        host->device copies execute in issue order, so the small uploads of an analysis (index matrices, V, weights)
+        must be issued before the 480 MB of X or they would wait behind it -- and with them the first kernels."""
+        n, p = int(Xh.shape[0]), int(Xh.shape[1])
+        self._x_host = Xh            # keep the pinned source alive until the copies have been consumed
+        self._pending = []           # empty list = upload not started yet
+        return torch.empty((n, p), dtype=F64, device=self.device)
+
+    def _start_upload(self):
+        if self._pending is None or len(self._pending) > 0:
+            return
+        Xh, Xd = self._x_host, self._X
+        n, p = int(Xh.shape[0]), int(Xh.shape[1])
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        side = self._copy_stream
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        step = -(-p // self.UPLOAD_CHUNKS)
+        step = -(-step // 256) * 256                  # whole pairs of 128-voxel tiles
+        pend = []
+        with torch.cuda.device(self.device):
+            for v0 in range(0, p, step):
+                v1 = min(p, v0 + step)
+                # (torch's copy_ of a column block goes through a contiguous temporary and synchronises)
+                check(lib.plsb200_copy2d_h2d(Xd.data_ptr() + 8 * v0, 8 * p, Xh.data_ptr() + 8 * v0, 8 * p,
+                                             8 * (v1 - v0), n, side.cuda_stream), "copy2d_h2d")
+                ev = torch.cuda.Event()
+                ev.record(side)
+                pend.append((v0, v1, ev))
+        Xd.record_stream(side)
+        self._pending = pend
+
     def _upload_x(self, X):
         """X -> device.  In a multi-process run X is replicated (every rank is handed the same host matrix), so
         each rank uploads only its 1/world share of the rows over PCIe and the ranks exchange the shares with one
@@ -60,6 +121,9 @@ class Engine:
         from . import dist
         size = dist.world()[1]
         on_host = not (torch.is_tensor(X) and X.is_cuda)
+        if (size == 1 and on_host and torch.is_tensor(X) and X.dim() == 2 and X.dtype == F64 and X.is_pinned()
+                and X.is_contiguous() and X.numel() * 8 >= self.PIPELINED_UPLOAD_MIN_BYTES):
+            return self._upload_pipelined(X)
         if size == 1 or not on_host or len(X.shape) != 2:
             return self.to_device(X, F64)
         n = int(X.shape[0])
@@ -161,7 +225,16 @@ class Engine:
     def G(self):
         """G = X X^T (N x N), computed once per engine."""
         if self._G is None:
-            self._G = self.gram_of(self.X)
+            if self._pending is None:
+                self._G = self.gram_of(self.X)
+            else:       # partial Gram matrices of the voxel ranges as they arrive, summed in a fixed order
+                cur = torch.cuda.current_stream(self.device)
+                G = None
+                for v0, v1, ev in self._x_ranges():
+                    cur.wait_event(ev)
+                    Gc = self.gram_of(self._X[:, v0:v1])
+                    G = Gc if G is None else G.add_(Gc)
+                self._G = G
         return self._G
 
     def xv(self, V):
@@ -263,36 +336,47 @@ class Engine:
                                                self._stream()), "coef_project_f64")
         return C2
 
-    KMAX = 24   # columns per boot_moments launch
 
-    @property
-    def ximage(self):
-        """TF32 hi/lo planes of X in the tile order of the tcgen05 kernel (fast mode), built once per engine."""
+    def _ximage_of(self, i, v0, v1, ev):
+        """TF32 hi/lo planes of the voxel range [v0, v1) of X in the tile order of the tcgen05 kernel (fast mode),
+        built once per engine and range."""
         if self._ximage is None:
+            self._ximage = {}
+        if i not in self._ximage:
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
             with torch.cuda.device(self.device):
-                img = self._ws(lib.plsb200_tf32_ximage_bytes(self.N, self.p))
-                check(lib.plsb200_tf32_split_x(self._p(self.X), self.N, self.p, self.ldx, self._p(img), self._stream()),
-                      "tf32_split_x")
-            self._ximage = img
-        return self._ximage
+                img = self._ws(lib.plsb200_tf32_ximage_bytes(self.N, v1 - v0))
+                check(lib.plsb200_tf32_split_x(self._X.data_ptr() + 8 * v0, self.N, v1 - v0, self.ldx,
+                                               self._p(img), self._stream()), "tf32_split_x")
+            self._ximage[i] = (v0, v1, img)
+        return self._ximage[i][2]
 
     def _boot_moments_tf32(self, E, idx, pivot, R, K):
         with torch.cuda.device(self.device):
             nbytes = lib.plsb200_boot_coef_bytes_tf32(self.N, K, R)
             if nbytes == 0:
                 raise _lib.PlsB200Error(f"boot_moments (tf32x3): unsupported shape N={self.N} K={K} R={R}")
-            img = self.ximage
             coef = self._ws(nbytes)
             check(lib.plsb200_boot_coef_pack_tf32(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
                                                   self._stream()), "boot_coef_pack_tf32")
-            ws = self._ws(lib.plsb200_boot_moments_tf32_workspace(self.N, self.p, K, R))
             s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
-            self._mark("boot_moments")
-            check(lib.plsb200_boot_moments_tf32(self._p(img), self.N, self.p, self._p(coef), K, R, self._p(pivot),
-                                                self._p(s1), self._p(s2), self._p(ws), ws.numel(), self._stream()),
-                  "boot_moments_tf32")
-            self._mark("boot_moments")
+            # the voxel ranges of the first call stay the unit of work for later calls (their images are cached)
+            if getattr(self, "_tf32_ranges", None) is None:
+                self._tf32_ranges = self._x_ranges()
+            for i, (v0, v1, ev) in enumerate(self._tf32_ranges):
+                img = self._ximage_of(i, v0, v1, ev)         # split of range i, then straight away its GEMM
+                pc = v1 - v0
+                ws = self._ws(lib.plsb200_boot_moments_tf32_workspace(self.N, pc, K, R))
+                self._mark("boot_moments")
+                check(lib.plsb200_boot_moments_tf32(self._p(img), self.N, pc, self._p(coef), K, R,
+                                                    None if pivot is None else pivot.data_ptr() + 8 * v0 * K,
+                                                    s1.data_ptr() + 8 * v0 * K, s2.data_ptr() + 8 * v0 * K,
+                                                    self._p(ws), ws.numel(), self._stream()), "boot_moments_tf32")
+                self._mark("boot_moments")
         return s1, s2
+
+    KMAX = 24   # columns per boot_moments launch
 
     def boot_moments(self, E, idx, pivot=None):
         """K4: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 with VS_r = X^T scatter(E, idx_r); p x K each."""
@@ -307,6 +391,7 @@ class Engine:
                 parts.append(self.boot_moments(E[:, sl].contiguous(), idx,
                                                None if pivot is None else pivot[:, sl].contiguous()))
             return torch.cat([a for a, _ in parts], dim=1), torch.cat([b for _, b in parts], dim=1)
+        self._x_ranges()          # (starts a deferred upload of X now: every small input is already on its way)
         if self.precision == "tf32x3":
             return self._boot_moments_tf32(E, idx, pivot, R, K)
         with torch.cuda.device(self.device):
@@ -316,13 +401,19 @@ class Engine:
             coef = self._ws(nbytes)
             check(lib.plsb200_boot_coef_pack_f64(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
                                                  self._stream()), "boot_coef_pack_f64")
-            ws = self._ws(lib.plsb200_boot_moments_f64_workspace(self.N, self.p, K, R))
             s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
-            self._mark("boot_moments")
-            check(lib.plsb200_boot_moments_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(coef), K, R,
-                                               self._p(pivot), self._p(s1), self._p(s2), self._p(ws), ws.numel(),
-                                               self._stream()), "boot_moments_f64")
-            self._mark("boot_moments")
+            cur = torch.cuda.current_stream(self.device)
+            for v0, v1, ev in self._x_ranges():          # one launch per voxel range still arriving, else one in all
+                if ev is not None:
+                    cur.wait_event(ev)
+                pc = v1 - v0
+                ws = self._ws(lib.plsb200_boot_moments_f64_workspace(self.N, pc, K, R))
+                self._mark("boot_moments")
+                check(lib.plsb200_boot_moments_f64(self._X.data_ptr() + 8 * v0, self.N, pc, self.ldx, self._p(coef),
+                                                   K, R, None if pivot is None else pivot.data_ptr() + 8 * v0 * K,
+                                                   s1.data_ptr() + 8 * v0 * K, s2.data_ptr() + 8 * v0 * K,
+                                                   self._p(ws), ws.numel(), self._stream()), "boot_moments_f64")
+                self._mark("boot_moments")
         return s1, s2
 
     def boot_finalize(self, s1, s2, R_total, numer=None):

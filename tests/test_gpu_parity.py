@@ -216,3 +216,41 @@ def test_multiblock_methods_match_reference_golden(name):
     np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(rt.conf_ints_T[0][:, live], g["conf_T_lo"][:, live], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(rt.conf_ints_T[1][:, live], g["conf_T_hi"][:, live], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "tf32x3"])
+def test_pipelined_upload_gives_the_same_results(precision):
+    """A large pinned host X is uploaded in voxel ranges while the bootstrap moment GEMM already runs on the ranges
+    that have arrived (Engine._upload_pipelined): same results as with X resident on the device."""
+    import torch
+    from plspy_b200 import bootstrap_permutation as bp, class_functions as cf, resample
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(12)
+    groups, C, p = (10, 10), 3, 150_000                      # 60 x 150000 doubles = 72 MB >= the pipelining threshold
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)); X[:10, :2000] += 0.8
+    co = np.array([[n] * C for n in groups])
+    _, X_mc = cf._mean_centre(X, co, 0)
+    U, s, V = cf._run_pls(X_mc)
+    Tvsc = cf._get_group_condition_means(X @ V, co)
+    np.random.seed(3)
+    ip = resample.permutation_indices("mct", 30, co)[0]; ib = resample.bootstrap_indices("mct", 30, co)[0]
+    Xh = torch.from_numpy(X).pin_memory()
+    out = []
+    for src in (Xh, Xh.cuda()):
+        eng = Engine(src, precision=precision)
+        assert eng.upload_in_flight == (not src.is_cuda)
+        rt = bp.ResampleTest._create("mct", src, None, U, s.copy(), V, co, 0, preprocess=cf._mean_centre, nperm=30,
+                                     nboot=30, Tvsc_orig=Tvsc, CI=0.95, perm_indices=ip, boot_indices=ib, engine=eng)
+        assert not eng.upload_in_flight
+        out.append(rt)
+    a, b = out
+    np.testing.assert_array_equal(a.permute_ratio, b.permute_ratio)
+    np.testing.assert_allclose(a.perm_debug_dict["s_list"], b.perm_debug_dict["s_list"], rtol=1e-12)
+    live = np.abs(s) > 1e-8
+    tol = 1e-11 if precision == "fp64" else 1e-6
+    np.testing.assert_allclose(a.std_errs[:, live], b.std_errs[:, live], rtol=tol)
+    np.testing.assert_allclose(a.boot_ratios[:, live], b.boot_ratios[:, live], rtol=tol)
+    np.testing.assert_allclose(a.conf_ints[0][:, live], b.conf_ints[0][:, live], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(a.boot_debug_dict["left_sv_sampled"], b.boot_debug_dict["left_sv_sampled"], rtol=1e-10,
+                               atol=1e-12)
