@@ -55,12 +55,14 @@ static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, 
     r.npass = (int)cdiv(K, r.kcp);
     r.stage_doubles = (size_t)r.nks * r.nblk * 32 + (size_t)r.nks * 4;
     r.warps = r.nks <= 32 ? 16 : 8;
-    const size_t fixed = ((size_t)16 + 2 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 16) * sizeof(double) + 256;
-    int ns = (int)((225 * 1024 - fixed) / (r.stage_doubles * sizeof(double)));
+    // weight ring (4 slots), block sizes, running moments, per-warp scale / moment tables, barriers
+    const size_t fixed = ((size_t)4 * r.nks * 4 + 16 + 2 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 24) * sizeof(double) + 256;
+    const size_t coef_bytes = (size_t)r.nks * r.nblk * 32 * sizeof(double);
+    int ns = (int)((225 * 1024 - fixed) / coef_bytes);
     if (ns > 4) ns = 4;
     if (ns < 2) return false;
     r.nstage = ns;
-    r.smem_bytes = ns * r.stage_doubles * sizeof(double) + fixed;
+    r.smem_bytes = ns * coef_bytes + fixed;
     return true;
 }
 
@@ -119,14 +121,19 @@ template <int NKS, int NBLK, int W>
 __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
     constexpr int RD_WARPS = W, RD_THREADS = W * 32, RD_VOX = W * 8;
     extern __shared__ __align__(128) unsigned char smraw[];
-    constexpr int stage_doubles = NKS * NBLK * 32 + NKS * 4;
-    constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
-    double* ring = reinterpret_cast<double*>(smraw);
-    double* celln = ring + (size_t)a.nstage * stage_doubles;      // [RD_MAXCELL] rows per cell (negative: unit cell)
+    constexpr int coef_doubles = NKS * NBLK * 32;                 // B fragments of one bootstrap and pass
+    constexpr int w_doubles = NKS * 4;                            // its multiplicity weights, k-step order
+    constexpr int pack_doubles = coef_doubles + w_doubles;        // layout of one (bootstrap, pass) in `pack`
+    constexpr uint32_t coef_bytes = (uint32_t)coef_doubles * 8u, w_bytes = (uint32_t)w_doubles * 8u;
+    constexpr int WSLOTS = 4;
+    double* ring = reinterpret_cast<double*>(smraw);              // [nstage][coef_doubles]
+    double* wring = ring + (size_t)a.nstage * coef_doubles;       // [WSLOTS][w_doubles]
+    double* celln = wring + WSLOTS * w_doubles;                   // [RD_MAXCELL] rows per cell (negative: unit cell)
     double* acc = celln + RD_MAXCELL;                             // [2][NBLK*2][RD_THREADS] running moments
-    double* mom = acc + 2 * NBLK * 2 * RD_THREADS;                // [RD_WARPS][RD_MAXCELL][8 voxels][2] -> scale in [0]
-    uint64_t* full = reinterpret_cast<uint64_t*>(mom + RD_WARPS * RD_MAXCELL * 16);
+    double* tabs = acc + 2 * NBLK * 2 * RD_THREADS;               // per warp: scale[16][8], then (m1, m2)[16][8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + RD_WARPS * RD_MAXCELL * 24);
     uint64_t* empty = full + a.nstage;
+    uint64_t* wfull = empty + a.nstage;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = lane & 3, vr = lane >> 2;
@@ -135,22 +142,31 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
 
     if (tid == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, RD_WARPS); }
+        for (int s = 0; s < WSLOTS; ++s) mbar_init(wfull + s, 1);
         mbar_fence_init();
     }
     for (int i = tid; i < RD_MAXCELL; i += RD_THREADS) celln[i] = i < a.ncell ? a.celln[i] : 0.0;
     __syncthreads();
 
-    const size_t bstride = (size_t)a.npass * stage_doubles;       // doubles between consecutive bootstraps
-    auto issue = [&](int bb, int slot) {
-        mbar_expect_tx(full + slot, stage_bytes);
-        const char* src = reinterpret_cast<const char*>(a.pack + (size_t)bb * bstride + (size_t)a.pass * stage_doubles);
-        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+    const size_t bstride = (size_t)a.npass * pack_doubles;        // doubles between consecutive bootstraps
+    auto issue = [&](int bb, int slot) {                          // coefficients of bootstrap bb -> ring slot
+        mbar_expect_tx(full + slot, coef_bytes);
+        const char* src = reinterpret_cast<const char*>(a.pack + (size_t)bb * bstride + (size_t)a.pass * pack_doubles);
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * coef_doubles);
 #pragma unroll 1
-        for (uint32_t off = 0; off < stage_bytes; off += 16384u)
-            bulk_g2s(dst + off, src + off, min(16384u, stage_bytes - off), full + slot);
+        for (uint32_t off = 0; off < coef_bytes; off += 16384u)
+            bulk_g2s(dst + off, src + off, min(16384u, coef_bytes - off), full + slot);
     };
-    if (tid == 0)
+    auto issue_w = [&](int bb) {                                  // weights of bootstrap bb -> slot bb % WSLOTS
+        const int ws_ = bb % WSLOTS;
+        mbar_expect_tx(wfull + ws_, w_bytes);
+        bulk_g2s(wring + ws_ * w_doubles,
+                 a.pack + (size_t)bb * bstride + (size_t)a.pass * pack_doubles + coef_doubles, w_bytes, wfull + ws_);
+    };
+    if (tid == 0) {
+        for (int bb = 0; bb < min(WSLOTS, a.nbt); ++bb) issue_w(bb);
         for (int bb = 0; bb < min(a.nstage, a.nbt); ++bb) issue(bb, bb);
+    }
 
     double x[NKS];
 #pragma unroll
@@ -170,51 +186,61 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
             my1[(2 * j + e) * RD_THREADS] = live ? a.sum[v * a.Kfull + a.k0 + c] : 0.0;
             my2[(2 * j + e) * RD_THREADS] = live ? a.sumsq[v * a.Kfull + a.k0 + c] : 0.0;
         }
-    double* wm = mom + warp * (RD_MAXCELL * 16);                  // this warp's (cell, voxel) table
-    if ((warp >> 2) & 1) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the two warps of a sub-partition (see boot.cu)
+    double* sct = tabs + warp * (RD_MAXCELL * 24);                // scale[cell][voxel] of the current bootstrap
+    double* mt = sct + RD_MAXCELL * 8;                            // (m1, m2)[cell][voxel] of the next one
+    auto scales = [&]() {       // one (cell, voxel) pair per lane, no redundancy across the quad
+        __syncwarp();
+        for (int i = lane; i < a.ncell * 8; i += 32) sct[i] = rd_scale(mt[2 * i], mt[2 * i + 1], celln[i >> 3]);
+        __syncwarp();
+    };
+
+    // ---- weighted block moments of bootstrap 0 (later bootstraps: inside the DMMA loop of their predecessor)
+    mbar_wait(wfull + 0, 0u);
+    {
+        const volatile double* ws = wring + q;
+        double m1 = 0.0, m2 = 0.0;
+        int cell = 0;
+#pragma unroll
+        for (int s = 0; s < NKS; ++s) {
+            const double wx = ws[4 * s] * x[s];
+            m1 += wx;
+            m2 = fma(wx, x[s], m2);
+            if ((a.cend[s >> 5] >> (s & 31)) & 1u) {              // warp-uniform: last k-step of a cell
+                m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+                m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+                m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+                m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+                if (q == 0) { mt[(cell * 8 + vr) * 2] = m1; mt[(cell * 8 + vr) * 2 + 1] = m2; }
+                ++cell;
+                m1 = m2 = 0.0;
+            }
+        }
+    }
+    scales();
+    if ((warp >> 2) & 1) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the warps of a sub-partition (see boot.cu)
 
     int slot = 0, prev_slot = 0;
     uint32_t phase = 0, prev_phase = 0;
     for (int bb = 0; bb < a.nbt; ++bb) {
         if (tid == 0 && bb > 0) {
+            // every warp has finished iteration bb-1: its coefficient slot is free, and so are the weight slots of
+            // bootstraps <= bb (the weights of bootstrap j are read during iteration j-1); weights 0..3 were issued
+            // in the prologue, bootstrap bb+3 goes into the slot bootstrap bb-1 occupied
+            mbar_wait(empty + prev_slot, prev_phase);
             const int nx = bb - 1 + a.nstage;
-            if (nx < a.nbt) { mbar_wait(empty + prev_slot, prev_phase); issue(nx, prev_slot); }
+            if (nx < a.nbt) issue(nx, prev_slot);
+            if (bb + WSLOTS - 1 < a.nbt) issue_w(bb + WSLOTS - 1);
         }
         __syncwarp();
+        const bool has_next = bb + 1 < a.nbt;
+        if (has_next) mbar_wait(wfull + (bb + 1) % WSLOTS, (uint32_t)(((bb + 1) / WSLOTS) & 1));
         mbar_wait(full + slot, phase);
-        const volatile double* bs = ring + (size_t)slot * stage_doubles + lane;
-        const volatile double* ws = ring + (size_t)slot * stage_doubles + NKS * NBLK * 32 + q;
+        const volatile double* bs = ring + (size_t)slot * coef_doubles + lane;
+        const volatile double* ws = wring + ((bb + 1) % WSLOTS) * w_doubles + q;     // (stale but harmless when !has_next)
 
-        // ---- pass 1: weighted block moments m1 = sum w x, m2 = sum w x^2 per cell (FMA on the resident fragments)
-        {
-            double m1 = 0.0, m2 = 0.0;
-            int cell = 0;
-#pragma unroll
-            for (int s = 0; s < NKS; ++s) {
-                const double wx = ws[4 * s] * x[s];
-                m1 += wx;
-                m2 = fma(wx, x[s], m2);
-                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {        // warp-uniform: last k-step of a cell
-                    m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
-                    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-                    m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
-                    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-                    if (q == 0) { wm[(cell * 8 + vr) * 2] = m1; wm[(cell * 8 + vr) * 2 + 1] = m2; }
-                    ++cell;
-                    m1 = m2 = 0.0;
-                }
-            }
-        }
-        __syncwarp();
-        // ---- scales: one (cell, voxel) pair per lane, no redundancy across the quad
-        for (int i = lane; i < a.ncell * 8; i += 32) {
-            const double sc = rd_scale(wm[2 * i], wm[2 * i + 1], celln[i >> 3]);
-            wm[2 * i] = sc;
-        }
-        __syncwarp();
-
-        // ---- pass 2: P_c = X_c^T Q_c on the tensor cores, folded into VS with the cell's scale
-        double d[NBLK][2], vs[NBLK][2];
+        // ---- P_c = X_c^T Q_c of bootstrap bb on the tensor cores, folded into VS with the cell's scale; in the
+        //      shadow of the DMMAs, the weighted block moments of bootstrap bb+1 on the same resident fragments
+        double d[NBLK][2], vs[NBLK][2], m1 = 0.0, m2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NBLK; ++j) { d[j][0] = d[j][1] = 0.0; vs[j][0] = vs[j][1] = 0.0; }
         {
@@ -226,9 +252,18 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                     const double b = bs[(s * NBLK + j) * 32];
                     dmma884(d[j][0], d[j][1], x[s], b);
                 }
-                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {
-                    const double sc = wm[(cell * 8 + vr) * 2];
+                const double wx = ws[4 * s] * x[s];
+                m1 += wx;
+                m2 = fma(wx, x[s], m2);
+                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {          // warp-uniform: last k-step of a cell
+                    const double sc = sct[cell * 8 + vr];
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+                    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+                    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+                    if (q == 0) { mt[(cell * 8 + vr) * 2] = m1; mt[(cell * 8 + vr) * 2 + 1] = m2; }
                     ++cell;
+                    m1 = m2 = 0.0;
 #pragma unroll
                     for (int j = 0; j < NBLK; ++j) {
                         vs[j][0] = fma(sc, d[j][0], vs[j][0]);
@@ -260,6 +295,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                     a.Npart[((size_t)bb * (8 * NBLK) + c) * ((size_t)gridDim.x * RD_WARPS) + blockIdx.x * RD_WARPS + warp] = n2;
                 if (a.VSt && ok) a.VSt[((size_t)bb * (8 * NBLK) + c) * a.p + v] = val;
             }
+        if (has_next) scales();                                   // scales of bootstrap bb+1 from its moments
         prev_slot = slot; prev_phase = phase;
         if (++slot == a.nstage) { slot = 0; phase ^= 1u; }
     }
