@@ -13,8 +13,9 @@
 //     the MMA descriptors address, so a pipeline stage is two contiguous chunks moved by 1-D bulk copies
 //     (cp.async.bulk, TMA engine) -- no tensor maps.  Per stage: Xh, Xl (128 x 16) and Ch, Cl (ntile x 16), six
 //     MMAs (three products x two k-steps of 8).
-//   * warp 0 = bulk-copy producer, warp 1 = MMA issuer (one thread) + TMEM allocator, warps 2-5 = epilogue
-//     (tcgen05.ld 32x32b -> FADD pivot -> F2F -> DADD/DFMA).
+//   * warps 0-3 = epilogue (tcgen05.ld 32x32b -> FADD pivot -> FP32 tile sums -> FP64 running moments), warp 4 =
+//     bulk-copy producer, warp 5 = MMA issuer (one thread) + TMEM allocator: the two single-thread roles carry the
+//     highest warp ids of their schedulers, which the issue arbiter favours over the epilogue warps they share with.
 //   * persistent CTAs, one per SM; work unit = (voxel tile, contiguous range of column tiles); units are ordered
 //     so that CTAs running concurrently stream the same coefficient range (L2-resident).
 #include "common.cuh"
@@ -52,9 +53,10 @@ static bool tf_plan(int N, int K, int R, int64_t p, TfPlan& t) {
     t.nct = (int)cdiv(R, t.nres);
     t.b_plane = (uint32_t)t.ntile * TF_KB * 4;
     const char* env = getenv("PLSB200_TF32_CTA_GROUP");
-    // default: single CTA (measured 26.3-26.7 ms on the bench workload vs 26.9-27.8 ms for the pair, which moves a
-    // third less data through L2 / shared memory but is held back by the tensor pipe all the same)
-    t.cg = (env && env[0] == '2') ? 2 : 1;
+    // default: CTA pairs (23.4 ms on the bench workload vs 24.2 ms single-CTA once the epilogue stopped being the
+    // limiter: the pair moves a third less data through L2 and shared memory); PLSB200_TF32_CTA_GROUP=1 selects the
+    // single-CTA kernel
+    t.cg = (env && env[0] == '1') ? 1 : 2;
     t.stage_bytes = TF_A_STAGE + 2 * t.b_plane / t.cg;
     int ns = (int)((227 * 1024 - 2048) / t.stage_bytes);
     if (ns > 8) ns = 8;
@@ -219,6 +221,8 @@ struct TfArgs {
     int K, R, nkb, nks_last, ntile, nres, nct, ct_per_split, nstage;
     uint32_t b_plane, stage_bytes;
     long long* trace;      // optional (PLSB200_TF32_TRACE=1): per-CTA cycle counters of the role loops, 8 per CTA
+    int dbg;               // development only (PLSB200_TF32_DEBUG): 1 = producer and MMA issuer free-running (no full /
+                           // empty hand-shake: wrong results, isolates contention from waiting), 2 = no producer at all
 };
 
 // ---- cluster helpers (CTA pair, cta_group::2)
@@ -246,9 +250,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
-template <int CG>
+// COLL: use of the tensor core's A-operand collector buffer -- 0 none, 1 fill (SASS A_KEEP: keep this A for the next MMA),
+// 2 lastuse (A_REUSE: take A from the collector instead of shared memory).  Of the three products of a k-step two share
+// the hi plane of X, so one of the three A reads from shared memory is saved.
+template <int CG, int COLL = 0>
 __device__ __forceinline__ void umma_tf32_cg(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (CG == 1) {
+    if constexpr (CG == 1 && COLL == 1) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if constexpr (CG == 1 && COLL == 2) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if constexpr (CG == 1) {
         umma_tf32(d_tmem, da, db, idesc, accumulate);
     } else {
         asm volatile(
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4 * CG); }
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == 5) {
         if constexpr (CG == 1) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -319,12 +338,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // ===================== producer: stream the operand images into the ring =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            long long w_empty = 0;
-            const long long t_begin = clock64();
             for (long long u = u_first; u < a.nunits; u += u_step) {
                 const long long vt = (u % a.nvt) * CG + rank;
                 const int split = (int)(u / a.nvt);
@@ -333,9 +350,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 for (int ct = ct0; ct < ct1; ++ct) {
                     const char* bsrc = reinterpret_cast<const char*>(a.bimg) + (size_t)ct * a.nkb * (2u * a.b_plane);
                     for (int kb = 0; kb < a.nkb; ++kb) {
-                        const long long tw = clock64();
-                        mbar_wait(empty + stage, phase ^ 1u);
-                        w_empty += clock64() - tw;
+                        if (a.dbg == 2 || a.dbg == 4) continue;
+                        if (a.dbg == 0 || a.dbg == 3 || a.dbg == 5) mbar_wait(empty + stage, phase ^ 1u);
                         unsigned char* dst = ring + (size_t)stage * a.stage_bytes;
                         mbar_expect_tx(full + stage, cta_stage_bytes);
                         bulk_g2s(dst, asrc + (size_t)kb * TF_A_STAGE, TF_A_STAGE, full + stage);
@@ -347,45 +363,46 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     }
                 }
             }
-            if (a.trace) { a.trace[blockIdx.x * 8 + 4] = clock64() - t_begin; a.trace[blockIdx.x * 8 + 5] = w_empty; }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         if (lane == 0 && rank == 0) {
             // ===================== MMA issuer (single thread of the leader CTA) =====================
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.ntile >> 3) << 17) |
                                    ((uint32_t)((128 * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-            const uint32_t ring_s = smem_u32(ring);
-            long long w_full = 0, w_pfull = 0, w_tempty = 0;
-            const long long t_begin = clock64();
+            // descriptors differ only in their 14-bit start-address field (bytes >> 4): one base per operand plane,
+            // per-stage and per-k-step offsets are plain adds (the ring lies below 256 KB, so the field cannot overflow)
+            const uint64_t d_ah = umma_desc_sw64(smem_u32(ring));
+            const uint64_t d_al = d_ah + (TF_A_PLANE >> 4), d_bh = d_ah + (TF_A_STAGE >> 4), d_bl = d_bh + (bhalf >> 4);
+            const uint64_t stage_step = a.stage_bytes >> 4;
+            const int last_kb = a.nkb - 1;
             for (long long u = u_first; u < a.nunits; u += u_step) {
                 const int split = (int)(u / a.nvt);
                 const int ct0 = split * a.ct_per_split, ct1 = min(a.nct, ct0 + a.ct_per_split);
                 for (int ct = ct0; ct < ct1; ++ct) {
-                    long long tw = clock64();
                     if constexpr (CG == 2) mbar_wait_cluster(tempty + as, aphase ^ 1u);
                     else mbar_wait(tempty + as, aphase ^ 1u);
-                    w_tempty += clock64() - tw;
                     tc_fence_after();
                     const uint32_t d = tbase + (uint32_t)as * 256u;
-                    for (int kb = 0; kb < a.nkb; ++kb) {
-                        tw = clock64();
-                        mbar_wait(full + stage, phase);
-                        const long long tw2 = clock64();
-                        if constexpr (CG == 2) mbar_wait_cluster(pfull + stage, phase);
-                        w_full += tw2 - tw;
-                        w_pfull += clock64() - tw2;
+                    uint32_t accum = 0u;
+                    for (int kb = 0; kb <= last_kb; ++kb) {
+                        if (a.dbg == 0 || a.dbg == 3 || a.dbg == 5) {
+                            mbar_wait(full + stage, phase);
+                            if constexpr (CG == 2) mbar_wait_cluster(pfull + stage, phase);
+                        }
                         tc_fence_after();
-                        const uint32_t sa = ring_s + (uint32_t)stage * a.stage_bytes;
-                        const uint32_t sb = sa + TF_A_STAGE;
-                        const int nks = (kb == a.nkb - 1) ? a.nks_last : 2;
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t ah = umma_desc_sw64(sa + ks * 32u), al = umma_desc_sw64(sa + TF_A_PLANE + ks * 32u);
-                            const uint64_t bh = umma_desc_sw64(sb + ks * 32u), bl = umma_desc_sw64(sb + bhalf + ks * 32u);
-                            // small cross terms first, leading term last
-                            umma_tf32_cg<CG>(d, ah, bl, idesc, (kb | ks) ? 1u : 0u);
-                            umma_tf32_cg<CG>(d, al, bh, idesc, 1u);
-                            umma_tf32_cg<CG>(d, ah, bh, idesc, 1u);
+                        const uint64_t so = (uint64_t)stage * stage_step;
+                        const uint64_t ah = d_ah + so, al = d_al + so, bh = d_bh + so, bl = d_bl + so;
+                        // the two products with the hi plane of X back to back: the second takes A from the collector
+                        // buffer instead of shared memory
+                        umma_tf32_cg<CG, 1>(d, ah, bl, idesc, accum);
+                        umma_tf32_cg<CG, 2>(d, ah, bh, idesc, 1u);
+                        umma_tf32_cg<CG, 0>(d, al, bh, idesc, 1u);
+                        accum = 1u;
+                        if (kb != last_kb || a.nks_last == 2) {          // second k-step of 8 rows (32 bytes further)
+                            umma_tf32_cg<CG, 1>(d, ah + 2, bl + 2, idesc, 1u);
+                            umma_tf32_cg<CG, 2>(d, ah + 2, bh + 2, idesc, 1u);
+                            umma_tf32_cg<CG, 0>(d, al + 2, bh + 2, idesc, 1u);
                         }
                         umma_commit_cg<CG>(empty + stage);       // frees the smem slot (in both CTAs) once read
                         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
@@ -393,10 +410,6 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     umma_commit_cg<CG>(tfull + as);              // accumulator complete -> epilogue(s)
                     if (++as == 2) { as = 0; aphase ^= 1u; }
                 }
-            }
-            if (a.trace) {
-                long long* t = a.trace + blockIdx.x * 8;
-                t[0] = clock64() - t_begin; t[1] = w_full; t[2] = w_pfull; t[3] = w_tempty;
             }
         } else if (CG == 2 && lane == 0) {
             // ===================== relay (rank 1): tell the leader that my stage has landed =====================
@@ -418,8 +431,6 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
         const int row = quarter * 32 + lane;
         int as = 0; uint32_t aphase = 0;
         const uint32_t tempty0 = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : smem_u32(tempty);
-        long long w_tfull = 0;
-        const long long t_begin = clock64();
         for (long long u = u_first; u < a.nunits; u += u_step) {
             const long long vt = (u % a.nvt) * CG + rank;
             const int split = (int)(u / a.nvt);
@@ -433,46 +444,69 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 s1[k] = 0.0; s2[k] = 0.0;
             }
             for (int ct = ct0; ct < ct1; ++ct) {
-                const long long tw = clock64();
                 mbar_wait(tfull + as, aphase);
-                w_tfull += clock64() - tw;
                 tc_fence_after();
                 const uint32_t t0 = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
                 const int nvalid = min(a.nres, a.R - ct * a.nres) * KP;     // valid columns of this tile
-                if (nvalid == a.ntile) {
-                    for (int per = 0; per < a.ntile; per += P) {
+                if (a.dbg == 5) {
+                    // development only: all the tensor-memory loads of a tile, none of the arithmetic
+                    for (int c0 = 0; c0 < a.ntile; c0 += 16) {
+                        uint32_t x[16];
+                        tmem_ld16(t0 + (uint32_t)c0, x);
+                        tmem_ld_wait();
+                        s1[0] += (double)__uint_as_float(x[c0 & 15]);
+                    }
+                } else if (a.dbg >= 3) {
+                    // development only: drain the accumulator without the FP64 fold
+                    uint32_t x[16];
+                    tmem_ld16(t0, x);
+                    tmem_ld_wait();
+                    s1[0] += (double)__uint_as_float(x[0]);
+                } else {
+                    // The <= 128 resamples of one tile are summed in FP32 (pivot-centred values: |d| ~ the bootstrap
+                    // spread, 20 terms at K = 12 -> relative error ~1e-7), the tile sums are folded into the FP64
+                    // running moments: one F2F / DADD pair per k and tile instead of one per element.  (With the FP64
+                    // fold per element the epilogue warps slowed the MMAs down by 13 %.)
+                    float f1[KP], f2[KP];
 #pragma unroll
-                        for (int q = 0; q < NCH; ++q) {
-                            uint32_t x[16];
-                            tmem_ld16(t0 + (uint32_t)(per + 16 * q), x);
-                            tmem_ld_wait();
+                    for (int k = 0; k < KP; ++k) { f1[k] = 0.f; f2[k] = 0.f; }
+                    if (nvalid == a.ntile) {
+                        for (int per = 0; per < a.ntile; per += P) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                const int k = (16 * q + e) % KP;
-                                const double dv = (double)(__uint_as_float(x[e]) - piv[k]);
-                                s1[k] += dv;
-                                s2[k] = fma(dv, dv, s2[k]);
+                            for (int q = 0; q < NCH; ++q) {
+                                uint32_t x[16];
+                                tmem_ld16(t0 + (uint32_t)(per + 16 * q), x);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    const int k = (16 * q + e) % KP;
+                                    const float dv = __uint_as_float(x[e]) - piv[k];
+                                    f1[k] += dv;
+                                    f2[k] = fmaf(dv, dv, f2[k]);
+                                }
                             }
                         }
-                    }
-                } else {
-                    for (int per = 0; per < nvalid; per += P) {
+                    } else {
+                        for (int per = 0; per < nvalid; per += P) {
 #pragma unroll
-                        for (int q = 0; q < NCH; ++q) {
-                            uint32_t x[16];
-                            tmem_ld16(t0 + (uint32_t)(per + 16 * q), x);
-                            tmem_ld_wait();
+                            for (int q = 0; q < NCH; ++q) {
+                                uint32_t x[16];
+                                tmem_ld16(t0 + (uint32_t)(per + 16 * q), x);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                const int k = (16 * q + e) % KP;
-                                if (per + 16 * q + e < nvalid) {
-                                    const double dv = (double)(__uint_as_float(x[e]) - piv[k]);
-                                    s1[k] += dv;
-                                    s2[k] = fma(dv, dv, s2[k]);
+                                for (int e = 0; e < 16; ++e) {
+                                    const int k = (16 * q + e) % KP;
+                                    if (per + 16 * q + e < nvalid) {
+                                        const float dv = __uint_as_float(x[e]) - piv[k];
+                                        f1[k] += dv;
+                                        f2[k] = fmaf(dv, dv, f2[k]);
+                                    }
                                 }
                             }
                         }
                     }
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) { s1[k] += (double)f1[k]; s2[k] += (double)f2[k]; }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -490,14 +524,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     if (k < a.K) { o1[k] = s1[k]; o2[k] = s2[k]; }
             }
         }
-        if (a.trace && warp == 2 && lane == 0) {
-            a.trace[blockIdx.x * 8 + 6] = clock64() - t_begin; a.trace[blockIdx.x * 8 + 7] = w_tfull;
-        }
     }
     __syncwarp();            // re-converge the warps whose lane 0 ran a role loop before the aligned barriers
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         __syncwarp();
         if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
         else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" ::"r"(tbase));
@@ -616,11 +647,7 @@ extern "C" int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, c
     a.K = K; a.R = R; a.nkb = t.nkb; a.nks_last = t.nks_last; a.ntile = t.ntile; a.nres = t.nres; a.nct = t.nct;
     a.ct_per_split = t.ct_per_split; a.nstage = t.nstage; a.b_plane = t.b_plane; a.stage_bytes = t.stage_bytes;
     a.trace = nullptr;
-    const bool trace = getenv("PLSB200_TF32_TRACE") != nullptr;
-    if (trace) {
-        PLSB_CUDA(cudaMalloc(&a.trace, 148 * 8 * sizeof(long long)));
-        PLSB_CUDA(cudaMemsetAsync(a.trace, 0, 148 * 8 * sizeof(long long), st));
-    }
+    a.dbg = getenv("PLSB200_TF32_DEBUG") ? atoi(getenv("PLSB200_TF32_DEBUG")) : 0;
     int rc;
     switch (t.Kp) {
 #define PLSB_TF(kp) case kp: rc = launch_tf32<kp>(t, a, st); break;
@@ -632,25 +659,6 @@ extern "C" int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, c
             return PLSB200_EUNSUPPORTED;
     }
     if (rc != PLSB200_OK) return rc;
-    if (trace) {      // development aid: synchronous dump of the role-loop cycle counters (mean over CTAs)
-        long long h[148 * 8];
-        PLSB_CUDA(cudaStreamSynchronize(st));
-        PLSB_CUDA(cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost));
-        cudaFree(a.trace);
-        double m[8] = {0};
-        int nmma = 0, nall = 0;
-        for (int c = 0; c < 148; ++c) {
-            if (h[c * 8 + 4] == 0) continue;
-            ++nall;
-            for (int j = 4; j < 8; ++j) m[j] += (double)h[c * 8 + j];
-            if (h[c * 8] != 0) { ++nmma; for (int j = 0; j < 4; ++j) m[j] += (double)h[c * 8 + j]; }
-        }
-        fprintf(stderr,
-                "[plsb200 tf32 trace] cg=%d nstage=%d | MMA thread: total %.0f cyc, wait full %.1f%%, wait peer-full %.1f%%, "
-                "wait tmem-empty %.1f%% | producer: total %.0f, wait empty %.1f%% | epilogue: total %.0f, wait tmem-full %.1f%%\n",
-                t.cg, t.nstage, m[0] / nmma, 100 * m[1] / m[0], 100 * m[2] / m[0], 100 * m[3] / m[0], m[4] / nall,
-                100 * m[5] / m[4], m[6] / nall, 100 * m[7] / m[6]);
-    }
     if (t.nsplit > 1) {
         const long long n = (long long)p * K;
         moments_reduce_tf32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(o1, o2, t.nsplit, n, sum, sumsq);
