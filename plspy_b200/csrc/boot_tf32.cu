@@ -315,6 +315,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    // (CTAs of a wave stream the same coefficient tiles at the same time on purpose: starting each group at a different
+    // column tile to spread the L2 load was measured 8 % SLOWER)
     const long long u_first = blockIdx.x / CG, u_step = gridDim.x / CG;
     const uint32_t bhalf = a.b_plane / CG;              // bytes of one coefficient plane staged by this CTA
     const uint32_t cta_stage_bytes = TF_A_STAGE + 2u * bhalf;
