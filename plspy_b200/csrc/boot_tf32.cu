@@ -57,6 +57,8 @@ static bool tf_plan(int N, int K, int R, int64_t p, TfPlan& t) {
     // limiter: the pair moves a third less data through L2 and shared memory); PLSB200_TF32_CTA_GROUP=1 selects the
     // single-CTA kernel
     t.cg = (env && env[0] == '1') ? 1 : 2;
+    const char* dbg = getenv("PLSB200_TF32_DEBUG");     // the no-producer probe modes only make sense without the relay
+    if (dbg && (dbg[0] == '2' || dbg[0] == '4')) t.cg = 1;
     t.stage_bytes = TF_A_STAGE + 2 * t.b_plane / t.cg;
     int ns = (int)((227 * 1024 - 2048) / t.stage_bytes);
     if (ns > 8) ns = 8;
