@@ -245,7 +245,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args._quiet.restore()
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -455,9 +456,33 @@ def run_gpu(args):
         "step_ms": step_log,
         "check": {"permute_ratio_lv0": float(rt.permute_ratio[0]), "boot_ratio_max": float(np.nanmax(np.abs(rt.boot_ratios[:, 0])))},
     }
-    print(json.dumps(line))
+    args._quiet.restore()
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)              # anything printed during teardown goes to stderr again
     if world > 1:
         dist.destroy_process_group()
+
+
+class _QuietStdout:
+    """Everything libraries write to file descriptor 1 while the benchmark runs (NCCL prints its version banner
+    there) goes to stderr instead; the descriptor is restored for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self._saved is not None:
+            sys.stdout.flush()
+            os.dup2(self._saved, 1)
+            os.close(self._saved)
+            self._saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
 
 
 def main():
@@ -475,12 +500,14 @@ def main():
                     help="fp64 = exact mode (headline); tf32x3 = fast mode only")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra fast-mode measurement")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        if args.warmup < 3:
-            args.warmup = 3
-        run_gpu(args)
+    with _QuietStdout() as quiet:
+        args._quiet = quiet
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            if args.warmup < 3:
+                args.warmup = 3
+            run_gpu(args)
 
 
 if __name__ == "__main__":
