@@ -1,0 +1,79 @@
+"""BASELINE.json's full-size target (mct, 3 groups x 25 subjects x 4 conditions x 200 000 voxels, 5000 permutations +
+5000 bootstraps) is far beyond what the oracle finishes in seconds, so parity at this size is checked through
+size-independent properties of the path:
+
+* homogeneity -- multiplying X by 2 (exact in binary floating point) must leave every permutation p-value and
+  every bootstrap ratio BIT-IDENTICAL and double every standard error exactly;
+* locality -- the standard errors of a block of voxels do not depend on the other voxels: an analysis of the first
+  4096 voxels with the same design weights reproduces the corresponding rows of the full run (1e-11; the resample
+  ranges are grouped differently, so not bit for bit);
+* the fast mode agrees with the exact mode within the north-star tolerance (bootstrap ratios 1e-4) and has
+  identical p-values."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GROUPS, C, P_VOX, NRES = (25, 25, 25), 4, 200_000, 5000
+
+
+@pytest.fixture(scope="module")
+def full():
+    import torch
+    from plspy_b200 import bootstrap_permutation as bp, class_functions as cf, resample
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(20260003)
+    N = sum(GROUPS) * C
+    X = rs.standard_normal((N, P_VOX))
+    X[:25, :10000] += 0.5
+    co = np.array([[n] * C for n in GROUPS])
+    _, X_mc = cf._mean_centre(X, co, 0)
+    U, s, V = cf._run_pls(X_mc)
+    Tvsc = cf._get_group_condition_means(X @ V, co)
+    np.random.seed(7)
+    ip = resample.permutation_indices("mct", NRES, co)[0]
+    ib = resample.bootstrap_indices("mct", NRES, co)[0]
+
+    def run(Xd, Vd, sv, precision="fp64"):
+        eng = Engine(Xd, precision=precision)
+        return bp.ResampleTest._create("mct", Xd, None, U, sv.copy(), Vd, co, 0, preprocess=cf._mean_centre, nperm=NRES,
+                                       nboot=NRES, Tvsc_orig=Tvsc, CI=0.95, perm_indices=ip, boot_indices=ib, engine=eng)
+    Xd = torch.from_numpy(X).cuda()
+    Vd = torch.from_numpy(np.ascontiguousarray(V)).cuda()
+    return dict(X=Xd, V=Vd, U=U, s=s, run=run, base=run(Xd, Vd, s), co=co, ib=ib, ip=ip, Tvsc=Tvsc)
+
+
+def test_full_size_homogeneity_is_exact(full):
+    a = full["base"]
+    b = full["run"](full["X"] * 2.0, full["V"], full["s"] * 2.0)       # V is unit-norm: X -> 2X doubles s only
+    live = full["s"] > 1e-8 * full["s"].max()     # (null LVs sit at the absolute 1e-12 threshold, which does not scale)
+    np.testing.assert_array_equal(a.permute_ratio[live], b.permute_ratio[live])
+    np.testing.assert_array_equal(2.0 * a.std_errs[:, live], b.std_errs[:, live])
+    np.testing.assert_array_equal(a.boot_ratios[:, live], b.boot_ratios[:, live])
+    np.testing.assert_array_equal(2.0 * a.perm_debug_dict["s_list"][:, live], b.perm_debug_dict["s_list"][:, live])
+
+
+def test_full_size_voxel_block_is_independent_of_the_rest(full):
+    import torch
+    from plspy_b200 import bootstrap_permutation as bp, class_functions as cf
+    from plspy_b200.engine import Engine
+    nv = 4096
+    Xs = full["X"][:, :nv].contiguous()
+    Vs = full["V"][:nv].contiguous()
+    eng = Engine(Xs)
+    rt = bp.ResampleTest._create("mct", Xs, None, full["U"], full["s"].copy(), Vs, full["co"], 0,
+                                 preprocess=cf._mean_centre, nperm=0, nboot=NRES, Tvsc_orig=full["Tvsc"], CI=0.95,
+                                 boot_indices=full["ib"], engine=eng)
+    live = full["s"] > 1e-8 * full["s"].max()
+    np.testing.assert_allclose(rt.std_errs[:, live], full["base"].std_errs[:nv][:, live], rtol=1e-11)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], full["base"].boot_ratios[:nv][:, live], rtol=1e-11)
+
+
+def test_full_size_fast_mode_within_tolerance(full):
+    f = full["run"](full["X"], full["V"], full["s"], precision="tf32x3")
+    a = full["base"]
+    live = full["s"] > 1e-8 * full["s"].max()
+    np.testing.assert_array_equal(a.permute_ratio, f.permute_ratio)
+    np.testing.assert_allclose(f.boot_ratios[:, live], a.boot_ratios[:, live], rtol=1e-4)
+    np.testing.assert_allclose(f.std_errs[:, live], a.std_errs[:, live], rtol=1e-4)
+    np.testing.assert_allclose(f.conf_ints[0], a.conf_ints[0], rtol=1e-12, atol=1e-12)     # N-space stays FP64
