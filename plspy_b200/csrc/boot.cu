@@ -335,12 +335,12 @@ __global__ void __launch_bounds__(128) salience_kernel(const double* __restrict_
 
 // XL = X . V : each CTA takes a chunk of XV_CHUNK voxels; the V chunk is staged transposed in shared memory
 // ([k][voxel]: conflict-free), a warp owns XV_RG rows at a time so that every V value fetched from shared
-// memory feeds XV_RG FMAs, lanes stride over the voxels (coalesced 256-B row segments of X), and the per-lane
+// memory feeds XV_RG FMAs (2: 24 accumulators keep the kernel at three CTAs per SM), lanes stride over the voxels (coalesced 256-B row segments of X), and the per-lane
 // partial sums are combined by shuffles in a fixed order (deterministic).  HBM-bound: X is read once.
 constexpr int XV_CHUNK = 512;
-constexpr int XV_RG = 4;
+constexpr int XV_RG = 2;
 template <int KT>
-__global__ void __launch_bounds__(256) xv_partial_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
+__global__ void __launch_bounds__(256, 3) xv_partial_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
                                                         const double* __restrict__ V, int K,
                                                         double* __restrict__ part) {
     extern __shared__ __align__(16) double smv[];   // [KT][XV_CHUNK]

@@ -37,7 +37,21 @@ __global__ void __launch_bounds__(512) nspace_kernel(const double* __restrict__ 
 #pragma unroll
             for (int t = 0; t < KT; ++t) acc[t] = 0.0;
             const int kn = min(KT, K - k0);
-            if (kn == KT) {
+            if (kn == KT && (K & 1) == 0) {
+                // full column group, even row stride: the broadcast reads of E go out as 16-byte loads (one LDS per two
+                // FMAs); the gathers of G rows are latency-bound (L2), so eight are kept in flight per thread
+#pragma unroll 8
+                for (int i = 0; i < N; ++i) {
+                    const double g = __ldg(G + (size_t)ids[i] * N + j);
+                    const double2* e2 = reinterpret_cast<const double2*>(Es + i * K + k0);
+#pragma unroll
+                    for (int t = 0; t < KT / 2; ++t) {
+                        const double2 ev = e2[t];
+                        acc[2 * t] = fma(g, ev.x, acc[2 * t]);
+                        acc[2 * t + 1] = fma(g, ev.y, acc[2 * t + 1]);
+                    }
+                }
+            } else if (kn == KT) {
 #pragma unroll 4
                 for (int i = 0; i < N; ++i) {
                     const double g = __ldg(G + (size_t)ids[i] * N + j);
