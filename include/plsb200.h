@@ -218,6 +218,19 @@ int plsb200_half_gram_f64(const double* Xstd, const double* Xlin, int64_t p, con
                           const int32_t* cells, int ncell, int unit_cells, int nmax, int K, int s0, int ns,
                           double* S3, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Windowed version of the same quantity (half_gram.cu; preferred, K <= 32): instead of `cells`, each half carries
+ * `nseg` segments  segs[h][s] = {pos_begin, pos_end, col0, width, unit, qoff}  (device, int32 x 6): the positions
+ * [pos_begin, pos_end) form one block (standardised over its member rows unless `unit`), and only the columns
+ * [col0, col0 + width), width <= 8, of Q are non-zero for them.  Inside the kernel a half's window coefficients
+ * are packed, wq = width rounded up to 1, 2, 4, 8 doubles per position; `qoff` is the (even) offset of the segment
+ * in that packing and `nq` (even) its total length in doubles.  Q keeps the dense S x 2 x nmax x K layout; columns
+ * outside the windows are not read.  Phase 1 costs `width` FMAs per position instead of K, the 2K x 2K Gram of a
+ * voxel tile runs on DMMA.                                                                                    */
+size_t plsb200_half_gram_win_f64_workspace(int64_t p, int K, int ns);
+int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin, int64_t p, const int32_t* ids, const double* Q,
+                              const int32_t* segs, int nseg, int nq, int nmax, int K, int s0, int ns, double* S3,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K3: batched symmetric eigensolver, one warp per K x K matrix (K <= 32), one-sided Jacobi with
  * shuffle-based rotations.  Replaces np.linalg.svd of the K x p half-sample cross-block matrices
  * (class_functions.py:122 as called from split_half_resampling.py:194,207,255,311,612-613,...) through

@@ -92,6 +92,9 @@ SIGNATURES = {
     "plsb200_half_gram_f64_workspace": (c_size_t, [c_int64, c_int, c_int]),
     "plsb200_half_gram_f64": (c_int, [c_double_p, c_double_p, c_int64, c_int32_p, c_double_p, c_int32_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_double_p, c_void_p, c_size_t, c_void_p]),
+    "plsb200_half_gram_win_f64_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "plsb200_half_gram_win_f64": (c_int, [c_double_p, c_double_p, c_int64, c_int32_p, c_double_p, c_int32_p, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_host_task_permutations": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                                c_void_p]),
     "plsb200_host_bootstrap_draws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,

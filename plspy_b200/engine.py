@@ -575,23 +575,61 @@ class Engine:
                                             self._p(cs), ncell, self._p(LV), self._stream()), "rb_lvcorr_f64")
         return LV
 
-    def half_gram(self, Xstd, Xlin, ids, Q, cells, unit_cells, max_ws_bytes=256 << 20):
+    def half_gram(self, Xstd, Xlin, ids, Q, cells, unit_cells, max_ws_bytes=256 << 20, dense=False):
         """Split-half Gram blocks in p-space: ids (S x 2 x nmax int32), Q (S x 2 x nmax x K),
-        cells (2 x (ncell+1) int32 position offsets).  Returns S3 (S x 3 x K x K) = [S11, S12, S22]."""
+        cells (2 x (ncell+1) int32 position offsets).  Returns S3 (S x 3 x K x K) = [S11, S12, S22].
+        The windowed kernel (half_gram.cu, DMMA Gram) is used: the non-zero column window of every block is read
+        off Q (blocks wider than 8 columns become several segments); `dense=True` forces the older FMA kernel of
+        rb.cu (K <= 24), kept as the in-library cross-check."""
         ids = self.to_device(ids, I32); Q = self.to_device(Q, F64)
-        cells = self.to_device(np.asarray(cells, dtype=np.int32), I32)
+        cells_h = np.asarray(cells.cpu() if torch.is_tensor(cells) else cells, dtype=np.int32)
         S, nmax, K = int(ids.shape[0]), int(ids.shape[2]), int(Q.shape[3])
-        ncell = int(cells.shape[1]) - 1
+        ncell = int(cells_h.shape[1]) - 1
         p = int(Xstd.shape[1])
         S3 = self._empty(S, 3, K, K)
-        per = lib.plsb200_half_gram_f64_workspace(p, K, 1)
+        if dense:
+            cells_d = self.to_device(cells_h, I32)
+            per = lib.plsb200_half_gram_f64_workspace(p, K, 1)
+            ns = max(1, min(S, int(max_ws_bytes // max(per, 1))))
+            with torch.cuda.device(self.device):
+                ws = self._ws(per * ns)
+                for s0 in range(0, S, ns):
+                    n = min(ns, S - s0)
+                    check(lib.plsb200_half_gram_f64(self._p(Xstd), self._p(Xlin), p, self._p(ids), self._p(Q),
+                                                    self._p(cells_d), ncell, int(unit_cells), nmax, K, s0, n,
+                                                    self._p(S3), self._p(ws), ws.numel(), self._stream()),
+                          "half_gram_f64")
+            return S3
+        nz = (Q != 0).any(dim=0).cpu().numpy()                      # 2 x nmax x K: columns a position ever feeds
+        segs = [[], []]       # (pos_begin, pos_end, col0, width, unit, offset of the packed coefficients in doubles)
+        nq = 2
+        for h in range(2):
+            off = 0
+            for c in range(ncell):
+                b, e = int(cells_h[h, c]), int(cells_h[h, c + 1])
+                cols = np.flatnonzero(nz[h, b:e].any(axis=0)) if e > b else []
+                if len(cols) == 0:
+                    continue
+                for c0 in range(int(cols[0]), int(cols[-1]) + 1, 8):
+                    w = min(8, int(cols[-1]) + 1 - c0)
+                    wq = 1 if w <= 1 else (2 if w == 2 else (4 if w <= 4 else 8))     # doubles per position
+                    segs[h].append((b, e, c0, w, int(c >= ncell - unit_cells), off))
+                    off += (e - b) * wq
+                    off += off & 1                                                   # 16-byte aligned segments
+            nq = max(nq, off)
+        nseg = max(len(segs[0]), len(segs[1]), 1)
+        table = np.zeros((2, nseg, 6), dtype=np.int32)
+        for h in range(2):
+            if segs[h]:
+                table[h, :len(segs[h])] = np.array(segs[h], dtype=np.int32)
+        segs_d = self.to_device(table, I32)
+        per = lib.plsb200_half_gram_win_f64_workspace(p, K, 1)
         ns = max(1, min(S, int(max_ws_bytes // max(per, 1))))
         with torch.cuda.device(self.device):
             ws = self._ws(per * ns)
             for s0 in range(0, S, ns):
                 n = min(ns, S - s0)
-                check(lib.plsb200_half_gram_f64(self._p(Xstd), self._p(Xlin), p, self._p(ids), self._p(Q),
-                                                self._p(cells), ncell, int(unit_cells), nmax, K, s0, n,
-                                                self._p(S3), self._p(ws), ws.numel(), self._stream()),
-                      "half_gram_f64")
+                check(lib.plsb200_half_gram_win_f64(self._p(Xstd), self._p(Xlin), p, self._p(ids), self._p(Q),
+                                                    self._p(segs_d), nseg, nq, nmax, K, s0, n, self._p(S3),
+                                                    self._p(ws), ws.numel(), self._stream()), "half_gram_win_f64")
         return S3

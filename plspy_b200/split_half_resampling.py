@@ -163,21 +163,28 @@ def _pspace_blocks(pls_alg, eng, Y, halves, co1, co2, mctype, contrasts, bscan):
         tcol = np.array([g * Kg + c for g in range(G) for c in range(C)])
         bcol = np.array([g * Kg + C + cb * nb + j for g in range(G) for cb in range(nbs) for j in range(nb)])
         K0 = G * Kg
-        cells, Q, ids = [], [], []
+        # The kernel forms the plain cell means of the half (one column per task cell); the centring operator of
+        # mb, A_h = Op_h @ Abar_h (its rows are constant within a cell), is applied to the K x K blocks afterwards.
+        cells, Q, ids, post = [], [], [], []
         for h, coh in ((1, co1), (2, co2)):
             cb_off = _offsets(coh[:, bs])
             nhb, nh = int(cb_off[-1]), int(coh.sum())
             Qb = eng.rb_coef(Y, halves["yb%d" % h], cb_off, np.eye(len(bcol)), scatter=False)[0]   # S x nhb x Kb
-            Ah = (class_functions._cell_mean_operator(coh) if pls_alg == "cmb"
-                  else class_functions._centring_operator(coh, mctype))                            # GC x nh
+            Abar = class_functions._cell_mean_operator(coh)                                        # GC x nh
             Qh = torch.zeros(S, nhb + nh, K0, dtype=torch.float64, device=eng.device)
             Qh[:, :nhb, torch.as_tensor(bcol, device=eng.device)] = Qb
-            Qh[:, nhb:, torch.as_tensor(tcol, device=eng.device)] = eng.to_device(np.ascontiguousarray(Ah.T),
+            Qh[:, nhb:, torch.as_tensor(tcol, device=eng.device)] = eng.to_device(np.ascontiguousarray(Abar.T),
                                                                                    torch.float64)
             Q.append(Qh)
-            cells.append(np.concatenate([cb_off, [nhb + nh]]).astype(np.int32))
+            t_off = _offsets(coh)
+            cells.append(np.concatenate([cb_off, nhb + t_off[1:]]).astype(np.int32))
             ids.append(np.concatenate([halves["xb%d" % h], halves["x%d" % h]], axis=1))
-        unit = 1
+            T = np.eye(K0)
+            if pls_alg == "mb":
+                Ah = class_functions._centring_operator(coh, mctype)
+                T[np.ix_(tcol, tcol)] = Ah[:, t_off[:-1]] * coh.reshape(-1)[None, :]     # Op = A[:, first pos of cell] n_cell
+            post.append(T)
+        unit = G * C
     nmax = max(int(ids[0].shape[1]), int(ids[1].shape[1]))
     ids_t = np.stack([_pad_cols(ids[0], nmax), _pad_cols(ids[1], nmax)], axis=1)                   # S x 2 x nmax
     Kq = int(Q[0].shape[2])
@@ -186,7 +193,11 @@ def _pspace_blocks(pls_alg, eng, Y, halves, co1, co2, mctype, contrasts, bscan):
     Qt[:, 1, :Q[1].shape[1]] = Q[1]
     ncell = len(cells[0]) - 1
     assert len(cells[1]) - 1 == ncell
-    S3 = eng.to_host(eng.half_gram(Xg, eng.X, ids_t, Qt, np.stack(cells), unit))
+    # mb: the centring operators annihilate constants, so the task cells can use the column-centred X as well
+    S3 = eng.to_host(eng.half_gram(Xg, Xg if pls_alg == "mb" else eng.X, ids_t, Qt, np.stack(cells), unit))
+    if multi and pls_alg == "mb":
+        T1, T2 = post
+        S3 = np.stack([T1 @ S3[:, 0] @ T1.T, T1 @ S3[:, 1] @ T2.T, T2 @ S3[:, 2] @ T2.T], axis=1)
     return S3
 
 

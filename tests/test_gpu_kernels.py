@@ -361,3 +361,70 @@ def test_rb_boot_dmma_chunked_launches_accumulate(torch_cuda):
     e2 = Engine(X2)
     s1, s2, T, n2 = e2.rb_boot(e2.X, e2.to_device(Q2, torch_cuda.float64), e2.to_device(W2, torch_cuda.float64), cs)
     assert np.isfinite(T.cpu().numpy()).all() and (n2.cpu().numpy() > 0).all()
+
+
+def _half_gram_numpy(Xstd, Xlin, ids, Q, cells, unit):
+    S, _, nmax, K = Q.shape
+    ncell = cells.shape[1] - 1
+    out = np.zeros((S, 3, K, K))
+    for s in range(S):
+        M = []
+        for h in range(2):
+            rows = np.zeros((K, Xstd.shape[1]))
+            for c in range(ncell):
+                b, e = cells[h, c], cells[h, c + 1]
+                if e <= b:
+                    continue
+                if c >= ncell - unit:
+                    blk = Xlin[ids[s, h, b:e]]
+                    rows += Q[s, h, b:e].T @ blk
+                else:
+                    blk = Xstd[ids[s, h, b:e]]
+                    sd = blk.std(axis=0)
+                    sc = np.where(sd > 0, 1.0 / (sd * np.sqrt(e - b)), 0.0)
+                    rows += (Q[s, h, b:e].T @ blk) * sc
+            M.append(rows)
+        out[s] = np.stack([M[0] @ M[0].T, M[0] @ M[1].T, M[1] @ M[1].T])
+    return out
+
+
+@pytest.mark.parametrize("p,K,width,ncell,unit,S", [
+    (1000, 24, 4, 6, 0, 5),      # behaviour layout: every block feeds its own 4 columns
+    (515, 24, 4, 8, 2, 4),       # multiblock-like: 6 standardised blocks + 2 plain blocks of width 1..4
+    (300, 12, 12, 3, 0, 3),      # dense contrasts: windows wider than 8 columns -> two segments per block
+    (129, 7, 1, 7, 7, 6),        # only plain blocks, K not a multiple of 8, one voxel into the second tile
+    (2000, 32, 8, 4, 0, 2),      # K = 32 (the Jacobi solver's limit)
+])
+def test_half_gram_windowed_matches_dense_kernel_and_numpy(torch_cuda, p, K, width, ncell, unit, S):
+    """half_gram.cu (column windows + DMMA Gram) against the dense FMA kernel of rb.cu and numpy, unequal halves"""
+    import torch
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(p + K)
+    sizes = [rs.randint(3, 12, size=ncell), rs.randint(3, 12, size=ncell)]
+    cells = np.stack([np.concatenate(([0], np.cumsum(sz))) for sz in sizes]).astype(np.int32)
+    nmax = int(cells[:, -1].max())
+    N = 2 * nmax + 3
+    X = rs.standard_normal((N, p)) + 2.0
+    Xc = X - X.mean(axis=0)
+    ids = np.zeros((S, 2, nmax), np.int32)
+    Q = np.zeros((S, 2, nmax, K))
+    for s in range(S):
+        perm = rs.permutation(N)
+        for h in range(2):
+            nh = cells[h, -1]
+            ids[s, h, :nh] = perm[h * nmax: h * nmax + nh]
+            for c in range(ncell):
+                b, e = cells[h, c], cells[h, c + 1]
+                c0 = (c * width) % max(K - width + 1, 1)
+                Q[s, h, b:e, c0:c0 + width] = rs.standard_normal((e - b, width))
+    eng = Engine(X)
+    Xd, Xcd = eng.X, torch.from_numpy(Xc).cuda()
+    ref = _half_gram_numpy(Xc, X, ids, Q, cells, unit)
+    scale = np.abs(ref).max()
+    got = eng.half_gram(Xcd, Xd, ids, Q, cells, unit).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-11 * scale)
+    again = eng.half_gram(Xcd, Xd, ids, Q, cells, unit, max_ws_bytes=1).cpu().numpy()      # one split per launch
+    np.testing.assert_array_equal(again, got)
+    if K <= 24:
+        dense = eng.half_gram(Xcd, Xd, ids, Q, cells, unit, dense=True).cpu().numpy()
+        np.testing.assert_allclose(got, dense, rtol=1e-10, atol=1e-12 * scale)
