@@ -435,13 +435,15 @@ class Engine:
             check(lib.plsb200_colstd_f64(self._p(A), R, M, self._p(out), self._stream()), "colstd_f64")
         return out
 
-    def salience(self, E, idx):
-        """Explicit VS[r] = X^T scatter(E, idx_r) (R x p x K) -- small problems only."""
+    def salience(self, E, idx, M=None):
+        """Explicit VS[r] = M^T scatter(E, idx_r) (R x p x K), M = X by default -- small R only."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        M = self.X if M is None else M
+        n, p, ld = int(M.shape[0]), int(M.shape[1]), int(M.stride(0))
         R, K = int(idx.shape[0]), int(E.shape[1])
-        out = self._empty(R, self.p, K)
+        out = self._empty(R, p, K)
         with torch.cuda.device(self.device):
-            check(lib.plsb200_salience_f64(self._p(self.X), self.N, self.p, self.ldx, self._p(E), K, self._p(idx), R,
+            check(lib.plsb200_salience_f64(self._p(M), n, p, ld, self._p(E), K, self._p(idx), R,
                                            self._p(out), self._stream()), "salience_f64")
         return out
 

@@ -20,7 +20,9 @@ def PLS(*args, **kwargs):
     `boot_indices` (pre-generated resampling index matrices), `engine` (an `Engine` already holding X),
     `precision` ("fp64" = exact mode, default; "tf32x3" = fast mode for the bootstrap moment GEMM),
     `rotate_method` (2 = derived, the reference's behaviour and the default; 1 = Procrustes; 0 = per-permutation SVD,
-    mct only -- see `_ResampleTestPLS._permutation_test`).
+    mct only -- see `_ResampleTestPLS._permutation_test`), `analysis` ("host" = LAPACK on the cross-block matrix as
+    in the reference, default; "device" = through the Gram matrix on the GPU, mct / cst / rb / csb, sign of each
+    latent variable fixed by convention -- see device_analysis.py).
     """
     pls_method = kwargs.pop("pls_method", "mct")
     kwargs["pls_alg"] = pls_method

@@ -11,7 +11,7 @@ import abc
 
 import numpy as np
 
-from . import bootstrap_permutation, class_functions, exceptions, split_half_resampling
+from . import bootstrap_permutation, class_functions, device_analysis, exceptions, split_half_resampling
 
 
 class PLSBase(abc.ABC):
@@ -44,7 +44,7 @@ class PLSBase(abc.ABC):
         return cls._subclasses[pls_method](*args, **kwargs)
 
     # ---- shared helpers -------------------------------------------------------------------
-    _ENGINE_KWARGS = ("perm_indices", "boot_indices", "engine", "device", "precision", "rotate_method")
+    _ENGINE_KWARGS = ("perm_indices", "boot_indices", "engine", "device", "precision", "rotate_method", "analysis")
 
     def _take_kwargs(self, kwargs):
         self.pls_alg = kwargs["pls_alg"]
@@ -123,9 +123,26 @@ class PLSBase(abc.ABC):
         self.Xbscan = self.X[mask]
         self.Ybscan = self.Y[mask]
 
+    def _device_analysis(self):
+        """True when `analysis="device"` was requested: the one-off analysis then runs through the Gram matrix on the
+        GPU (device_analysis.py) and `self._engine_kwargs["engine"]` holds the engine with X."""
+        mode = self._engine_kwargs.get("analysis", "host")
+        if mode not in ("host", "device"):
+            raise ValueError('analysis must be "host" or "device"')
+        if mode == "host":
+            return False
+        if self.pls_alg in ("mb", "cmb"):
+            raise exceptions.NotImplementedError('analysis="device" is provided for mct, cst, rb and csb')
+        if self._engine_kwargs.get("engine") is None:
+            from .engine import Engine
+            self._engine_kwargs["engine"] = Engine(self.X, device=self._engine_kwargs.get("device"),
+                                                   precision=self._engine_kwargs.get("precision", "fp64"))
+        return True
+
     def _resample(self, Y, mctype, preprocess, **kw):
+        V = getattr(self, "_V_dev", None)
         self.resample_tests = bootstrap_permutation.ResampleTest._create(
-            self.pls_alg, self.X, Y, self.U, self.s, self.V, self.cond_order, mctype, preprocess=preprocess,
+            self.pls_alg, self.X, Y, self.U, self.s, self.V if V is None else V, self.cond_order, mctype, preprocess=preprocess,
             nperm=self.num_perm, nboot=self.num_boot, CI=self.CI,
             perm_indices=self._engine_kwargs.get("perm_indices"),
             boot_indices=self._engine_kwargs.get("boot_indices"),
@@ -175,10 +192,15 @@ class _MeanCentreTaskPLS(PLSBase):
         self._set_design(X, Y, groups_sizes, num_conditions, cond_order, need_y=False)
         self.num_perm, self.num_boot, self.CI = num_perm, num_boot, CI
         self._set_mctype(num_conditions, mctype)
-        self.X_means, self.X_mc = class_functions._mean_centre(self.X, self.cond_order, mctype=self.mctype)
-        self.U, self.s, self.V = class_functions._run_pls(self.X_mc)
-        self.X_latent = class_functions._compute_X_latents(self.X, self.V)
-        Tvsc_orig = class_functions._get_group_condition_means(self.X_latent, self.cond_order)
+        if self._device_analysis():
+            a = device_analysis.task(self._engine_kwargs["engine"], self.cond_order, self.mctype)
+            self.X_means, self.X_mc, self.U, self.s, self.V = a["X_means"], a["X_mc"], a["U"], a["s"], a["V"]
+            self.X_latent, Tvsc_orig, self._V_dev = a["X_latent"], a["Tvsc_orig"], a["V_dev"]
+        else:
+            self.X_means, self.X_mc = class_functions._mean_centre(self.X, self.cond_order, mctype=self.mctype)
+            self.U, self.s, self.V = class_functions._run_pls(self.X_mc)
+            self.X_latent = class_functions._compute_X_latents(self.X, self.V)
+            Tvsc_orig = class_functions._get_group_condition_means(self.X_latent, self.cond_order)
         self._resample(None, self.mctype, class_functions._mean_centre, Tvsc_orig=Tvsc_orig)
         self._split_half(None, self.mctype, None)
         self._finish()
@@ -196,9 +218,14 @@ class _RegularBehaviourPLS(PLSBase):
         self._set_design(X, Y, groups_sizes, num_conditions, cond_order, need_y=True)
         self._check_behaviour(self.Y, self.cond_order)
         self.num_perm, self.num_boot, self.CI = num_perm, num_boot, CI
-        self.R = class_functions._compute_R(self.X, self.Y, self.cond_order)
-        self.U, self.s, self.V = class_functions._run_pls(self.R)
-        self.X_latent = class_functions._compute_X_latents(self.X, self.V)
+        if self._device_analysis():
+            a = device_analysis.behaviour(self._engine_kwargs["engine"], self.Y, self.cond_order)
+            self.R, self.U, self.s, self.V, self.X_latent, self._V_dev = (a["R"], a["U"], a["s"], a["V"], a["X_latent"],
+                                                                          a["V_dev"])
+        else:
+            self.R = class_functions._compute_R(self.X, self.Y, self.cond_order)
+            self.U, self.s, self.V = class_functions._run_pls(self.R)
+            self.X_latent = class_functions._compute_X_latents(self.X, self.V)
         self.Y_latent = class_functions._compute_Y_latents(self.Y, self.U, self.cond_order)
         self.lvcorrs = class_functions._compute_R(self.X_latent, self.Y, self.cond_order)
         self._resample(self.Y, None, class_functions._compute_R, lvcorrs_orig=self.lvcorrs)
@@ -217,11 +244,16 @@ class _ContrastTaskPLS(PLSBase):
         self.contrasts = class_functions._normalize(contrasts)
         self.num_perm, self.num_boot, self.CI = num_perm, num_boot, CI
         self._set_mctype(num_conditions, mctype)
-        self.R = class_functions._get_group_condition_means(self.X, self.cond_order)
-        self.U, self.s, self.V = class_functions._run_pls_contrast(self.R, self.contrasts)
-        self.lvintercorrs = self.V.T @ self.V
-        self.X_latent = class_functions._compute_X_latents(self.X, class_functions._normalize(self.V))
-        Tvsc_orig = class_functions._get_group_condition_means(self.X_latent, self.cond_order)
+        if self._device_analysis():
+            a = device_analysis.contrast_task(self._engine_kwargs["engine"], self.cond_order, self.contrasts)
+            self.R, self.U, self.s, self.V, self.lvintercorrs = a["R"], a["U"], a["s"], a["V"], a["lvintercorrs"]
+            self.X_latent, Tvsc_orig, self._V_dev = a["X_latent"], a["Tvsc_orig"], a["V_dev"]
+        else:
+            self.R = class_functions._get_group_condition_means(self.X, self.cond_order)
+            self.U, self.s, self.V = class_functions._run_pls_contrast(self.R, self.contrasts)
+            self.lvintercorrs = self.V.T @ self.V
+            self.X_latent = class_functions._compute_X_latents(self.X, class_functions._normalize(self.V))
+            Tvsc_orig = class_functions._get_group_condition_means(self.X_latent, self.cond_order)
         self._resample(None, self.mctype, class_functions._mean_centre, contrast=self.contrasts,
                        Tvsc_orig=Tvsc_orig)
         self._split_half(None, self.mctype, self.contrasts)
@@ -239,10 +271,15 @@ class _ContrastBehaviourPLS(PLSBase):
         self.contrasts = class_functions._normalize(contrasts)
         self._check_behaviour(self.Y, self.cond_order)
         self.num_perm, self.num_boot, self.CI = num_perm, num_boot, CI
-        self.R = class_functions._compute_R(self.X, self.Y, self.cond_order)
-        self.U, self.s, self.V = class_functions._run_pls_contrast(self.R, self.contrasts)
-        self.lvintercorrs = self.V.T @ self.V
-        self.X_latent = class_functions._compute_X_latents(self.X, self.V)
+        if self._device_analysis():
+            a = device_analysis.contrast_behaviour(self._engine_kwargs["engine"], self.Y, self.cond_order, self.contrasts)
+            self.R, self.U, self.s, self.V, self.lvintercorrs = a["R"], a["U"], a["s"], a["V"], a["lvintercorrs"]
+            self.X_latent, self._V_dev = a["X_latent"], a["V_dev"]
+        else:
+            self.R = class_functions._compute_R(self.X, self.Y, self.cond_order)
+            self.U, self.s, self.V = class_functions._run_pls_contrast(self.R, self.contrasts)
+            self.lvintercorrs = self.V.T @ self.V
+            self.X_latent = class_functions._compute_X_latents(self.X, self.V)
         self.Y_latent = class_functions._compute_Y_latents(self.Y, self.U, self.cond_order)
         self._resample(self.Y, None, class_functions._compute_R, contrast=self.contrasts,
                        lvcorrs_orig=self.lvintercorrs)
@@ -252,6 +289,7 @@ class _ContrastBehaviourPLS(PLSBase):
 
 class _MultiblockCommon(PLSBase):
     def _multiblock_analysis(self, num_conditions, contrasts):
+        self._device_analysis()          # raises for analysis="device": host analysis only for the multiblock methods
         self._set_bscan()
         self._check_behaviour(self.Ybscan, self.cond_order[:, self.bscan])
         if contrasts is not None:

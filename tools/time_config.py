@@ -9,6 +9,7 @@ ap = argparse.ArgumentParser(); ap.add_argument("--cfg", type=int, default=2)
 ap.add_argument("--iters", type=float, default=1.0, help="scale factor on the iteration counts")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--precision", default="fp64")
+ap.add_argument("--analysis", default="host", help='"host" (LAPACK, reference signs) or "device" (through the Gram matrix)')
 ap.add_argument("--draw", action="store_true", help="let PLS() draw its own indices (native generator) instead of passing them in")
 a = ap.parse_args()
 rs = np.random.RandomState(20260000 + a.cfg)
@@ -41,15 +42,15 @@ else:
     ikw = dict(Y=Y)
 pi = resample.permutation_indices(method, P, co, **ikw); bi = resample.bootstrap_indices(method, B, co, **ikw)
 t_idx = time.perf_counter() - t0
-out = {"cfg": a.cfg, "method": method, "index_generation_s": t_idx}
+out = {"cfg": a.cfg, "method": method, "analysis": a.analysis, "precision": a.precision, "index_generation_s": t_idx}
 from plspy_b200 import _lib
 for rep in range(a.reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     if a.draw:
         np.random.seed(99)
-        res = plspy_b200.PLS(X, groups, C, precision=a.precision, **kw)
+        res = plspy_b200.PLS(X, groups, C, precision=a.precision, analysis=a.analysis, **kw)
     else:
-        res = plspy_b200.PLS(X, groups, C, perm_indices=pi, boot_indices=bi, precision=a.precision, **kw)
+        res = plspy_b200.PLS(X, groups, C, perm_indices=pi, boot_indices=bi, precision=a.precision, analysis=a.analysis, **kw)
     torch.cuda.synchronize(); out[f"pls_call_s_{rep}"] = time.perf_counter() - t0
 out["iters"] = [P, B, S]
 out["resamples_per_s_e2e"] = (P + B + 4 * S) / out[f"pls_call_s_{a.reps - 1}"]
