@@ -127,7 +127,7 @@ def _behaviour_state(eng, cells):
     return st
 
 
-def _multiblock_state(eng, cond_order, bscan):
+def _multiblock_state(eng, cond_order, bscan, keep_zb=False):
     """Per-engine cache for mb/cmb: the bscan rows of X block-centred (Xcb) and z-scored (Zb), the stacked
     matrices W1 = [X; Zb] (permutations, with its Gram matrix) and W2 = [Xcb; X] (bootstraps), and the
     column maps of the multiblock row order (per group: C task rows, then |bscan|*nb behaviour rows,
@@ -135,7 +135,7 @@ def _multiblock_state(eng, cond_order, bscan):
     co = np.asarray(cond_order)
     key = ("mb", tuple(co.reshape(-1).tolist()), tuple(bscan))
     st = getattr(eng, "_multiblock", None)
-    if st is not None and st["key"] == key:
+    if st is not None and st["key"] == key and (not keep_zb or "Zb" in st):
         return st
     rows_b = np.concatenate([np.full(co[g, c], c in list(bscan), dtype=bool)
                              for g in range(co.shape[0]) for c in range(co.shape[1])]).nonzero()[0]
@@ -145,6 +145,8 @@ def _multiblock_state(eng, cond_order, bscan):
     W1 = torch.cat([eng.X, Zb], dim=0)
     st = {"key": key, "rows_b": rows_b, "cells_b": cells_b, "Xcb": Xcb, "Nb": int(Xb.shape[0]),
           "Gw": eng.gram_of(W1), "W2": torch.cat([Xcb, eng.X], dim=0)}
+    if keep_zb:         # the device-side original analysis projects on Zb once more (device_analysis.multiblock)
+        st["Zb"] = Zb
     del W1, Zb, Xb
     eng._multiblock = st
     return st
@@ -178,19 +180,21 @@ def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast,
     nb = Ybscan.shape[1]
     tcol, bcol, K = _multiblock_columns(cond_order, bscan, nb)
     idx_t, idx_b = _multiblock_indices(pls_alg, indices, niter, cond_order, bscan, Ybscan, boot=False)
-    # rescaled observed singular values (:305-312); the un-normalised multiblock of the original data is a
-    # one-off host computation
-    raw = class_functions._create_multiblock(np.asarray(X) if not torch.is_tensor(X) else X.cpu().numpy(),
-                                             cond_order, pls_alg, bscan, mctype, norm_opt=False,
-                                             Xbscan=Xbscan, Ybscan=Ybscan)
-    org_s = np.sqrt(s ** 2 / np.sum(s ** 2) * np.sum(raw ** 2))
-    totcov_org = _stepdown_tail(org_s)
     Lop = (class_functions._cell_mean_operator(cond_order) if pls_alg == "cmb"
            else class_functions._centring_operator(cond_order, mctype))
+    N, Nb = eng.N, st["Nb"]
+    # rescaled observed singular values (:305-312): ||un-normalised multiblock of the original data||_F^2 is the sum
+    # of the quadratic forms of its rows' coefficients in Gw
+    C0 = np.zeros((N + Nb, K))
+    C0[:N, tcol] = Lop.T
+    C0[N:, bcol] = class_functions._behaviour_coefficients(Ybscan, np.asarray(cond_order)[:, list(bscan)])
+    C0 = eng.to_device(C0, torch.float64)
+    raw_sq = float(((st["Gw"] @ C0) * C0).sum())
+    org_s = np.sqrt(s ** 2 / np.sum(s ** 2) * raw_sq)
+    totcov_org = _stepdown_tail(org_s)
     Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
         np.asarray(contrast, dtype=float))
     Kc = Ucoef.shape[1]
-    N, Nb = eng.N, st["Nb"]
     lo, hi = dist.shard(niter)
     it = _index_shard(eng, idx_t, niter, lo, hi); ib = _index_shard(eng, idx_b, niter, lo, hi)
     R = hi - lo

@@ -114,6 +114,18 @@ def _block_zscore(M, cond_order):
     return Z
 
 
+def _behaviour_coefficients(Y, cond_order):
+    """Cy (N x G*C*nb): block c's rows carry its z-scored behaviours in columns c*nb .. c*nb+nb, so that
+    _compute_corr(X, Y) = Cy^T Z for the block z-scored X (class_functions.py:185-247)."""
+    starts, sizes = _cells(cond_order)
+    Yz = _block_zscore(Y, cond_order)
+    nb = Y.shape[1]
+    Cy = np.zeros((Y.shape[0], len(sizes) * nb))
+    for c, (st, n) in enumerate(zip(starts, sizes)):
+        Cy[st:st + n, c * nb:(c + 1) * nb] = Yz[st:st + n]
+    return Cy
+
+
 def _compute_corr(X, Y, cond_order):
     """Stacked per-block Pearson correlations (G*C*nb x p) (class_functions.py:185-247)."""
     starts, sizes = _cells(cond_order)

@@ -2,7 +2,7 @@
 SVD and the latent scores, for `PLS(..., analysis="device")`.
 
 The reference builds M on the host and calls LAPACK on it (pls_classes.py:258-266 mct, 576-586 rb, 854-866 cst,
-1131-1143 csb; class_functions.py:98-123 `_run_pls`, 126-162 `_run_pls_contrast`).  Here M is never the operand of a
+1131-1143 csb, 1441-1489 mb / cmb; class_functions.py:98-123 `_run_pls`, 126-162 `_run_pls_contrast`).  Here M is never the operand of a
 factorisation: every method's M is `Coef^T W` for a fixed coefficient matrix `Coef` (rows x K) and a data matrix W
 already on the device (X itself, or its block z-scored copy Z for the behaviour methods), so
 
@@ -60,8 +60,9 @@ def _project(eng, W, coef):
                      dim=1)
 
 
-def _svd_through_gram(eng, W, Gw, coef):
-    """U (K x K), s (K,), V (p x K, device) of M = coef^T W given Gw = W W^T."""
+def _svd_through_gram(eng, W, Gw, coef, project=None):
+    """U (K x K), s (K,), V (p x K, device) of M = coef^T W given Gw = W W^T; `project(c)` = W^T c when W is not
+    held as one matrix."""
     C = eng.to_device(coef, torch.float64)
     B = C.T @ Gw @ C
     B = 0.5 * (B + B.T)
@@ -74,7 +75,8 @@ def _svd_through_gram(eng, W, Gw, coef):
     s = np.sqrt(np.maximum(ev, 0.0))
     s = np.where(live, s, 0.0)
     inv = np.where(live, 1.0 / np.where(live, s, 1.0), 0.0)
-    V = _project(eng, W, np.asarray(coef) @ (U * inv))
+    cv = np.asarray(coef) @ (U * inv)
+    V = _project(eng, W, cv) if project is None else project(cv)
     return U, s, V
 
 
@@ -109,18 +111,6 @@ def contrast_task(eng, cond_order, contrasts):
     return dict(R=R, U=contrasts, s=s, V=Vh, V_dev=V, lvintercorrs=VtV, X_latent=XL, Tvsc_orig=Abar @ XL)
 
 
-def _behaviour_coef(Y, cond_order):
-    """Cy (N x G*C*nb): block c's rows carry its z-scored behaviours in columns c*nb .. c*nb+nb, so that
-    R = Cy^T Z for the block z-scored X (class_functions.py:185-247)."""
-    starts, sizes = cf._cells(cond_order)
-    Yz = cf._block_zscore(Y, cond_order)
-    nb = Y.shape[1]
-    Cy = np.zeros((Y.shape[0], len(sizes) * nb))
-    for c, (st, n) in enumerate(zip(starts, sizes)):
-        Cy[st:st + n, c * nb:(c + 1) * nb] = Yz[st:st + n]
-    return Cy
-
-
 def _behaviour_matrices(eng, cond_order):
     """Block z-scored X (Z, dense, this call only) and the per-engine cache holding Gz = Z Z^T for the permutations."""
     from .bootstrap_permutation import _cell_offsets
@@ -133,7 +123,7 @@ def _behaviour_matrices(eng, cond_order):
 def behaviour(eng, Y, cond_order):
     """rb (pls_classes.py:576-586): R, U, s, V (device), X_latent."""
     Z, Gz = _behaviour_matrices(eng, cond_order)
-    Cy = _behaviour_coef(Y, cond_order)
+    Cy = cf._behaviour_coefficients(Y, cond_order)
     U, s, V = _svd_through_gram(eng, Z, Gz, Cy)
     R = _project(eng, Z, Cy).T.contiguous()
     del Z
@@ -145,7 +135,7 @@ def behaviour(eng, Y, cond_order):
 def contrast_behaviour(eng, Y, cond_order, contrasts):
     """csb (pls_classes.py:1131-1143): R, U = contrasts, V = (C^T R)^T, s = its column norms, lvintercorrs = V^T V."""
     Z, Gz = _behaviour_matrices(eng, cond_order)
-    Cy = _behaviour_coef(Y, cond_order)
+    Cy = cf._behaviour_coefficients(Y, cond_order)
     E = Cy @ contrasts
     both = _project(eng, Z, np.concatenate([Cy, E], axis=1))
     del Z
@@ -158,3 +148,43 @@ def contrast_behaviour(eng, Y, cond_order, contrasts):
     XL = eng.xv(V)
     R, Vh, XL = eng.to_host(R, V, XL)
     return dict(R=R, U=contrasts, s=s, V=Vh, V_dev=V, lvintercorrs=VtV, X_latent=XL)
+
+
+def multiblock(eng, pls_alg, cond_order, mctype, bscan, Ybscan, contrasts=None):
+    """mb / cmb (pls_classes.py:1441-1489, 1799-1856; class_functions.py:454-516): the multiblock matrix (rows
+    L2-normalised), U, s, V (device) and X V.  With W = [X; Zb] (Zb = block z-scored bscan rows of X) the
+    un-normalised rows are C1^T W, their norms quadratic forms in Gw = W W^T."""
+    from .bootstrap_permutation import _multiblock_state, _multiblock_columns
+    co = np.asarray(cond_order)
+    st = _multiblock_state(eng, co, bscan, keep_zb=True)
+    N, Nb, Gw = eng.N, st["Nb"], st["Gw"]
+    tcol, bcol, K = _multiblock_columns(co, bscan, Ybscan.shape[1])
+    Lop = cf._cell_mean_operator(co) if pls_alg == "cmb" else cf._centring_operator(co, mctype)
+    C1 = np.zeros((N + Nb, K))
+    C1[:N, tcol] = Lop.T
+    C1[N:, bcol] = cf._behaviour_coefficients(Ybscan, co[:, list(bscan)])
+    C1d = eng.to_device(C1, torch.float64)
+    d2row = eng.to_host(((Gw @ C1d) * C1d).sum(dim=0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rn = np.where(d2row > 0, 1.0 / np.sqrt(np.where(d2row > 0, d2row, 1.0)), 0.0)
+    Cn = C1 * rn[None, :]                                          # normalised rows (norm_opt, :503-505)
+
+    def project(c):                                                # W^T c without holding W
+        c = np.asarray(c)
+        return _project(eng, eng.X, c[:N]) + _project(eng, st["Zb"], c[N:])
+    if contrasts is None:
+        U, s, V = _svd_through_gram(eng, None, Gw, Cn, project=project)
+        both = project(Cn)
+        M = both.T.contiguous()
+    else:
+        U = contrasts
+        E = Cn @ contrasts
+        both = project(np.concatenate([Cn, E], axis=1))
+        M, V = both[:, :K].T.contiguous(), both[:, K:].contiguous()
+        Ed = eng.to_device(E, torch.float64)
+        VtV = eng.to_host(Ed.T @ Gw @ Ed)
+        s = np.sqrt(np.maximum(np.diagonal(0.5 * (VtV + VtV.T)), 0.0))
+    XV = eng.xv(V)                                                 # X @ V (un-normalised V)
+    st.pop("Zb", None)
+    M, Vh, XV = eng.to_host(M, V, XV)
+    return dict(multiblock=M, U=U, s=s, V=Vh, V_dev=V, XV=XV, rows_b=st["rows_b"], raw_sq=float(d2row.sum()))

@@ -21,8 +21,8 @@ def PLS(*args, **kwargs):
     `precision` ("fp64" = exact mode, default; "tf32x3" = fast mode for the bootstrap moment GEMM),
     `rotate_method` (2 = derived, the reference's behaviour and the default; 1 = Procrustes; 0 = per-permutation SVD,
     mct only -- see `_ResampleTestPLS._permutation_test`), `analysis` ("host" = LAPACK on the cross-block matrix as
-    in the reference, default; "device" = through the Gram matrix on the GPU, mct / cst / rb / csb, sign of each
-    latent variable fixed by convention -- see device_analysis.py).
+    in the reference, default; "device" = through the Gram matrix on the GPU, sign of each latent
+    variable fixed by convention -- see device_analysis.py).
     """
     pls_method = kwargs.pop("pls_method", "mct")
     kwargs["pls_alg"] = pls_method

@@ -131,8 +131,6 @@ class PLSBase(abc.ABC):
             raise ValueError('analysis must be "host" or "device"')
         if mode == "host":
             return False
-        if self.pls_alg in ("mb", "cmb"):
-            raise exceptions.NotImplementedError('analysis="device" is provided for mct, cst, rb and csb')
         if self._engine_kwargs.get("engine") is None:
             from .engine import Engine
             self._engine_kwargs["engine"] = Engine(self.X, device=self._engine_kwargs.get("device"),
@@ -289,7 +287,6 @@ class _ContrastBehaviourPLS(PLSBase):
 
 class _MultiblockCommon(PLSBase):
     def _multiblock_analysis(self, num_conditions, contrasts):
-        self._device_analysis()          # raises for analysis="device": host analysis only for the multiblock methods
         self._set_bscan()
         self._check_behaviour(self.Ybscan, self.cond_order[:, self.bscan])
         if contrasts is not None:
@@ -301,14 +298,22 @@ class _MultiblockCommon(PLSBase):
             self.contrasts = class_functions._normalize(contrasts[keep, :])
         self._create_multiblock = class_functions._create_multiblock
         self._compute_corr = class_functions._compute_corr
-        self.multiblock = class_functions._create_multiblock(
-            self.X, self.cond_order, self.pls_alg, self.bscan, self.mctype, Xbscan=self.Xbscan, Ybscan=self.Ybscan)
-        if contrasts is not None:
-            self.U, self.s, self.V = class_functions._run_pls_contrast(self.multiblock, self.contrasts)
+        if self._device_analysis():
+            a = device_analysis.multiblock(self._engine_kwargs["engine"], self.pls_alg, self.cond_order, self.mctype,
+                                           self.bscan, self.Ybscan, self.contrasts if contrasts is not None else None)
+            self.multiblock, self.U, self.s, self.V, self._V_dev = a["multiblock"], a["U"], a["s"], a["V"], a["V_dev"]
+            nrm = np.linalg.norm(self.V, axis=0)
+            T_X_latent = a["XV"] * np.where(nrm > 0, 1.0 / np.where(nrm > 0, nrm, 1.0), 0.0)[None, :]
+            B_X_latent = a["XV"][a["rows_b"]]                 # Xbscan = the bscan rows of X
         else:
-            self.U, self.s, self.V = class_functions._run_pls(self.multiblock)
-        T_X_latent = class_functions._compute_X_latents(self.X, class_functions._normalize(self.V))
-        B_X_latent = class_functions._compute_X_latents(self.Xbscan, self.V)
+            self.multiblock = class_functions._create_multiblock(
+                self.X, self.cond_order, self.pls_alg, self.bscan, self.mctype, Xbscan=self.Xbscan, Ybscan=self.Ybscan)
+            if contrasts is not None:
+                self.U, self.s, self.V = class_functions._run_pls_contrast(self.multiblock, self.contrasts)
+            else:
+                self.U, self.s, self.V = class_functions._run_pls(self.multiblock)
+            T_X_latent = class_functions._compute_X_latents(self.X, class_functions._normalize(self.V))
+            B_X_latent = class_functions._compute_X_latents(self.Xbscan, self.V)
         self.X_latent = np.vstack((np.array(T_X_latent), np.array(B_X_latent)))
         self.usc, self.Tusc, self.Busc = self.X_latent, T_X_latent, B_X_latent
         Tu, Bu = class_functions._get_Tu_Bu(self.U, num_conditions, self.Y.shape[1], self.cond_order, self.bscan)

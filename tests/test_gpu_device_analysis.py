@@ -94,10 +94,39 @@ def test_csb_device_analysis_matches_reference():
     np.testing.assert_array_equal(res.resample_tests.permute_ratio, g["permute_ratio"])
 
 
-def test_device_analysis_is_refused_for_multiblock():
-    import plspy_b200
-    g = _load("mb_full")
-    with pytest.raises(plspy_b200.exceptions.NotImplementedError):
-        _run_product(g, analysis="device")
+@pytest.mark.parametrize("name", ["mb_full", "mb_bscan"])
+def test_mb_device_analysis_matches_reference_up_to_sign(name):
+    g = _load(name)
+    res = _run_product(g, analysis="device")
+    rt = res.resample_tests
+    live = np.abs(g["s"]) > 1e-8
+    np.testing.assert_allclose(res.multiblock, g["multiblock"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res.s[live], g["s"][live], rtol=1e-9)
+    sg = _signs(res, g, live)
+    np.testing.assert_allclose((res.V * sg)[:, live], g["V_design"][:, live], atol=1e-8)
+    np.testing.assert_allclose((res.U * sg)[:, live], g["U_brain"][:, live], atol=1e-8)
+    np.testing.assert_allclose((res.X_latent * sg)[:, live], g["X_latent"][:, live],
+                               atol=1e-8 * np.abs(g["X_latent"]).max())
+    np.testing.assert_allclose((res.lvcorrs * sg)[:, live], g["lvcorrs"][:, live], atol=1e-8)
+    np.testing.assert_array_equal(rt.permute_ratio[live], g["permute_ratio"][live])
+    np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-6)
+    np.testing.assert_allclose((rt.boot_ratios * sg)[:, live], g["boot_ratios"][:, live], rtol=1e-6, atol=1e-9)
+
+
+def test_cmb_device_analysis_matches_reference():
+    g = _load("cmb_full")
+    res = _run_product(g, analysis="device")
+    rt = res.resample_tests
+    np.testing.assert_allclose(res.multiblock, g["multiblock"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res.s, g["s"], rtol=1e-10)
+    np.testing.assert_allclose(res.U, g["U_brain"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res.X_latent, g["X_latent"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(res.lvcorrs, g["lvcorrs"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_array_equal(rt.permute_ratio, g["permute_ratio"])
+    np.testing.assert_allclose(rt.std_errs, g["std_errs"], rtol=1e-6)
+    np.testing.assert_allclose(rt.boot_ratios, g["boot_ratios"], rtol=1e-6, atol=1e-9)
+
+
+def test_device_analysis_rejects_unknown_mode():
     with pytest.raises(ValueError):
         _run_product(_load("mct_m0_bal"), analysis="gpu")
