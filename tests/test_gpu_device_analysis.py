@@ -130,3 +130,15 @@ def test_cmb_device_analysis_matches_reference():
 def test_device_analysis_rejects_unknown_mode():
     with pytest.raises(ValueError):
         _run_product(_load("mct_m0_bal"), analysis="gpu")
+
+
+def test_device_analysis_with_fast_mode():
+    """analysis="device" and precision="tf32x3" together: p-values exact, bootstrap ratios within the fast-mode tolerance"""
+    g = _load("mct_m0_bal")
+    res = _run_product(g, analysis="device", precision="tf32x3")
+    rt = res.resample_tests
+    live = np.abs(g["s"]) > 1e-8
+    sg = _signs(res, g, live)
+    np.testing.assert_array_equal(rt.permute_ratio, g["permute_ratio"])
+    np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-4)
+    np.testing.assert_allclose((rt.boot_ratios * sg)[:, live], g["boot_ratios"][:, live], rtol=1e-4, atol=1e-7)

@@ -77,3 +77,20 @@ def test_full_size_fast_mode_within_tolerance(full):
     np.testing.assert_allclose(f.boot_ratios[:, live], a.boot_ratios[:, live], rtol=1e-4)
     np.testing.assert_allclose(f.std_errs[:, live], a.std_errs[:, live], rtol=1e-4)
     np.testing.assert_allclose(f.conf_ints[0], a.conf_ints[0], rtol=1e-12, atol=1e-12)     # N-space stays FP64
+
+
+def test_full_size_device_analysis_agrees_with_lapack(full):
+    """the original analysis through the Gram matrix (analysis="device") at 300 x 200 000: singular values 1e-9,
+    brain-side vectors 1e-7 up to the sign of each latent variable"""
+    from plspy_b200 import device_analysis
+    from plspy_b200.engine import Engine
+    eng = Engine(full["X"])
+    a = device_analysis.task(eng, full["co"], 0)
+    s = full["s"]
+    live = s > 1e-8 * s.max()
+    assert np.all(a["s"][~live] == 0.0)
+    np.testing.assert_allclose(a["s"][live], s[live], rtol=1e-9)
+    Vh = full["V"].cpu().numpy()
+    sg = np.sign(np.sum(a["V"] * Vh, axis=0))
+    np.testing.assert_allclose((a["V"] * sg)[:, live], Vh[:, live], atol=1e-7 * np.abs(Vh).max())
+    np.testing.assert_allclose(np.abs(a["U"][:, live]), np.abs(full["U"][:, live]), atol=1e-7)
