@@ -325,6 +325,8 @@ class _ResampleTestPLS(ResampleTest):
         eng = engine if engine is not None else (
             Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
+        if eng is not None and self.pls_alg in ("mct", "cst") and dist.world()[1] > 1:
+            eng.gram_collective()          # all ranks are here: Gram from per-rank voxel ranges + one all-reduce
         perm_pending = None
         early = None
         if (eng is not None and eng.upload_in_flight and nboot > 0 and self.pls_alg in ("mct", "cst")

@@ -4,6 +4,8 @@ PyTorch is used for device memory, streams and (in `dist.py`) torch.distributed 
 produced by the hand-written kernels of libplsb200.so.  There is no CPU path: constructing an Engine
 without a CUDA device raises.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -236,6 +238,21 @@ class Engine:
                     G = Gc if G is None else G.add_(Gc)
                 self._G = G
         return self._G
+
+    def gram_collective(self):
+        """COLLECTIVE in a multi-process run (every rank must call it at the same point): G from the partial Gram
+        matrix of this rank's voxel range plus one all-reduce of N x N doubles, instead of every rank forming the whole
+        G redundantly -- the Gram is the largest piece of per-rank work that does not shrink with the shard of
+        resamples.  Single process, G already there, or PLSB200_SHARD_GRAM=0: the plain property."""
+        from . import dist
+        rank, size = dist.world()
+        if (self._G is None and size > 1 and self.p >= 4096 * size
+                and os.environ.get("PLSB200_SHARD_GRAM", "1") != "0"):
+            cut = [(self.p * r // size) // 64 * 64 for r in range(size)] + [self.p]
+            G = self.gram_of(self.X[:, cut[rank]:cut[rank + 1]])
+            dist.allreduce_sum_(G)
+            self._G = G
+        return self.G
 
     def xv(self, V):
         """XL = X @ V (N x K)."""
