@@ -370,8 +370,9 @@ def run_gpu(args):
                                                                         "e2e_ms", "rt"))
     value = units_step / (ms_step * 1e-3)
     d2h = (rt.std_errs.nbytes + rt.boot_ratios.nbytes + rt.conf_ints[0].nbytes * 2 + rt.permute_ratio.nbytes * 2
-           + rt.perm_debug_dict["s_list"].nbytes + rt.boot_debug_dict["left_sv_sampled"].nbytes
-           + rt.boot_debug_dict["Tdistrib"].nbytes)
+           + rt.perm_debug_dict["s_list"].nbytes)
+    if world == 1:      # multi-process runs leave the per-bootstrap distributions on the device until they are asked for
+        d2h += rt.boot_debug_dict["left_sv_sampled"].nbytes + rt.boot_debug_dict["Tdistrib"].nbytes
     e2e_value = units_step / (e2e_ms * 1e-3)
 
     if world > 1:

@@ -491,7 +491,11 @@ class _ResampleTestPLS(ResampleTest):
         Tdist = dist.gather_rows(Tdist, niter, lo)
         if left is not None:
             left = dist.gather_rows(left, niter, lo)
-        fetch_small = eng.to_host_async(eng.colstd(Tdist), Tdist, left, side=True)
+        # (multi-process runs gather R x K x K per family from every rank -- the whole job's, not the shard's -- so
+        # there only the standard deviations cross PCIe now and the distributions follow on first access)
+        defer = dist.world()[1] > 1
+        fetch_small = (eng.to_host_async(eng.colstd(Tdist), side=True) if defer
+                       else eng.to_host_async(eng.colstd(Tdist), Tdist, left, side=True))
         if _early is not None:
             s1, s2 = _early
         elif hi > lo:
@@ -502,14 +506,19 @@ class _ResampleTestPLS(ResampleTest):
         std_errs, boot_ratios = eng.boot_finalize(s1, s2, niter, numer=numer)   # (:695-703)
         z = norm.ppf(1 - (1 - CI) / 2)                                      # (:709)
         std_errs_h, boot_ratios_h = eng.to_host(std_errs, boot_ratios)
-        std_T, Tdist_h, left_h = fetch_small()
+        std_T, Tdist_h, left_h = (fetch_small(), None, None) if defer else fetch_small()
         half = std_T * z                                                    # (:715-716)
         conf_int = (Tvsc_orig - half, Tvsc_orig + half)
 
         debug = _LazyDebugDict()
-        debug["left_sv_sampled"] = (left_h if left_h is not None
-                                    else np.zeros((niter, Ucoef.shape[0], Ucoef.shape[1])))
-        debug["Tdistrib"] = Tdist_h
+        if defer:
+            debug.set_lazy("Tdistrib", lambda: eng.to_host(Tdist))
+            debug.set_lazy("left_sv_sampled", (lambda: eng.to_host(left)) if left is not None
+                           else (lambda: np.zeros((niter, Ucoef.shape[0], Ucoef.shape[1]))))
+        else:
+            debug["left_sv_sampled"] = (left_h if left_h is not None
+                                        else np.zeros((niter, Ucoef.shape[0], Ucoef.shape[1])))
+            debug["Tdistrib"] = Tdist_h
         debug.set_lazy("indices", lambda: _indices_to_host(indices, niter))
 
         def _right():   # the reference's B x p x K cube, only on request
