@@ -1,5 +1,4 @@
 """Device time of the N-space pass (K2/K6) at the bench shape: 5000 resamples, N = 300, K = 12 (development aid).
-PLSB200_NSPACE_BATCH=0 selects the one-resample-per-CTA kernel.
 
     PYTHONPATH=. python tools/time_nspace.py
 """
