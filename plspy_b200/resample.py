@@ -222,3 +222,21 @@ def resample_with_replacement(matrix, cond_order, C=None, group_num=0, return_in
     idx = _bootstrap_draw(_subject_grids(cond_order))
     out = np.asarray(matrix)[idx, :]
     return (out, idx) if return_indices else out
+
+
+def confidence_interval(matrix, conf=(0.05, 0.95)):
+    """Element-wise percentile interval over the first axis of a (B, m, n) stack, MATLAB `prctile` convention
+    (sample k of the sorted values sits at 100 (k + 0.5) / B per cent, linear interpolation, clamped to the extremes)
+    -- resample.py:171-222 of the reference, which loops over the m x n elements; here one sort along the stack axis
+    and one vectorised interpolation.  Returns (lower, upper), each m x n."""
+    a = np.sort(np.asarray(matrix, dtype=float), axis=0)
+    B = a.shape[0]
+
+    def at(q):
+        t = q * B - 0.5                                     # fractional index into the sorted samples
+        t = min(max(t, 0.0), B - 1.0)
+        lo = int(np.floor(t))
+        hi = min(lo + 1, B - 1)
+        w = t - lo
+        return a[lo] * (1.0 - w) + a[hi] * w
+    return at(conf[0]), at(conf[1])

@@ -225,3 +225,21 @@ def test_native_index_generator_ragged_design_uses_numpy():
     pos = ctypes.c_int32(624); out = np.zeros((1, 7), np.int32)
     assert lib.plsb200_host_task_permutations(key.ctypes.data, ctypes.addressof(pos), co.ctypes.data, 1, 2, 0, 1,
                                               out.ctypes.data, None) == -4
+
+
+def test_confidence_interval_matches_the_elementwise_loop():
+    """plspy_b200.resample.confidence_interval (vectorised) against a restatement of the reference's element loop
+    (resample.py:171-222: percentile positions 100 (k + 0.5) / B, np.interp, extremes clamped)"""
+    from plspy_b200 import resample
+    rs = np.random.RandomState(5)
+    for B in (1, 2, 7, 100):
+        M = rs.standard_normal((B, 3, 4))
+        for conf in ((0.05, 0.95), (0.0, 1.0), (0.5, 0.5), (0.001, 0.999), (0.3, 0.31)):
+            lo, hi = resample.confidence_interval(M, conf)
+            for i in range(3):
+                for j in range(4):
+                    X = np.sort(M[:, i, j])
+                    x = np.concatenate(([0], (np.arange(0.5, B - 0.5 + 1) / B) * 100, [100]))
+                    y = np.concatenate(([X.min()], X, [X.max()]))
+                    np.testing.assert_allclose(lo[i, j], np.interp(conf[0] * 100, x, y), rtol=1e-12, atol=1e-14)
+                    np.testing.assert_allclose(hi[i, j], np.interp(conf[1] * 100, x, y), rtol=1e-12, atol=1e-14)
