@@ -71,7 +71,7 @@ def _worker(rank, world, port, out):
 
 def test_sharded_reduction_world2():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # no fork() of this (multi-threaded) test process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     spans = [out[r] for r in range(world)]
