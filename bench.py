@@ -198,10 +198,10 @@ def blas_threads():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(X, groups, C, n_each, seed=7):
-    """Times the oracle port of the reference loops (same per-iteration structure as
-    plspy/core/bootstrap_permutation.py:323-452, 537-675) on `n_each` permutations and `n_each`
-    bootstraps of the full-size workload; returns (resamples/s, seconds, description)."""
+def port_rate(X, groups, C, n_each, seed=7):
+    """Second CPU figure: the oracle PORT of the reference loops (same per-iteration structure as
+    plspy/core/bootstrap_permutation.py:323-452, 537-675, but with running moments instead of the B x p x K cube) on
+    `n_each` permutations and `n_each` bootstraps of the full-size workload."""
     import oracle
     co = np.array([[n] * C for n in groups])
     a = oracle.analysis("mct", X, groups, C, mctype=MCTYPE)
@@ -218,35 +218,156 @@ def cpu_reference_rate(X, groups, C, n_each, seed=7):
     desc = (f"{n_each} permutations ({(t1 - t0) / n_each * 1e3:.0f} ms each) + {n_each} bootstraps "
             f"({(t2 - t1) / n_each * 1e3:.0f} ms each) of the full-size workload, oracle port of the reference "
             f"loops (numpy {np.__version__}), right_sv_sampled not materialised")
-    return 2 * n_each / dt, dt, desc
+    return {"value": 2 * n_each / dt, "unit": UNIT, "kind": "port", "sample": desc, "seconds": dt}
+
+
+class _IndexRecorder:
+    """Records the index vectors the reference's own resamplers draw (plspy/core/resample.py:9-165), so that the
+    GPU path can be run on exactly the resamples the reference sample used."""
+
+    def __init__(self, plspy):
+        self.res = plspy.core.resample
+        self.perm, self.boot = [], []
+        self._owr, self._wr = self.res.resample_without_replacement, self.res.resample_with_replacement
+
+    def __enter__(self):
+        rec = self
+
+        def owr(matrix, cond_order, C=None, group_num=0, return_indices=False, pls_alg="mct"):
+            out, inds = rec._owr(matrix, cond_order, C, group_num, True, pls_alg)
+            rec.perm.append(np.asarray(inds, dtype=np.int32).copy())
+            return (out, inds) if return_indices else out
+
+        def wr(matrix, cond_order, C=None, group_num=0, return_indices=False):
+            out, inds = rec._wr(matrix, cond_order, C, group_num, True)
+            rec.boot.append(np.asarray(inds, dtype=np.int32).copy())
+            return (out, inds) if return_indices else out
+        self.res.resample_without_replacement, self.res.resample_with_replacement = owr, wr
+        return self
+
+    def __exit__(self, *a):
+        self.res.resample_without_replacement, self.res.resample_with_replacement = self._owr, self._wr
+
+
+def reference_available():
+    import baseline
+    return baseline.reference_available()
+
+
+def reference_sample(X, groups, C, n_perm, n_boot, seed=7, analysis=None):
+    """Times the UNMODIFIED reference (baseline/_ref/plspy, pip-installed from /root/reference) through its own seam:
+    `ResampleTest._create("mct", X, None, U, s, V, cond_order, mctype, preprocess=_mean_centre, nperm=, nboot=, ...)`
+    (plspy/core/bootstrap_permutation.py:53-63, 139-263; the call of pls_classes.py:268-282), once with
+    (n_perm, 0) and once with (0, n_boot), on the full-size X.  The one-off analysis (its `_mean_centre`, `_run_pls`,
+    latents) is outside the timed region, as in the GPU arm.  Returns timings, the reference's results and the index
+    vectors its resamplers drew."""
+    import contextlib
+    import baseline
+    plspy = baseline.import_reference()
+    cf, rbp = plspy.core.class_functions, plspy.core.bootstrap_permutation
+    co = np.array([[n] * C for n in groups])
+    if analysis is None:
+        _, X_mc = cf._mean_centre(X, co, mctype=MCTYPE)
+        U, s, V = cf._run_pls(X_mc)
+        Tvsc = cf._get_group_condition_means(cf._compute_X_latents(X, V), co)
+        analysis = (U, s, V, Tvsc)
+    U, s, V, Tvsc = analysis
+    np.random.seed(seed)
+    out = {"analysis": analysis}
+    with _IndexRecorder(plspy) as rec, open(os.devnull, "w") as sink, contextlib.redirect_stdout(sink):
+        t0 = time.perf_counter()
+        if n_perm:
+            out["perm"] = rbp.ResampleTest._create("mct", X, None, U, s.copy(), V, co, MCTYPE, preprocess=cf._mean_centre,
+                                                   nperm=n_perm, nboot=0, Tvsc_orig=Tvsc, CI=0.95)
+        t1 = time.perf_counter()
+        if n_boot:
+            out["boot"] = rbp.ResampleTest._create("mct", X, None, U, s.copy(), V, co, MCTYPE, preprocess=cf._mean_centre,
+                                                   nperm=0, nboot=n_boot, Tvsc_orig=Tvsc, CI=0.95)
+        t2 = time.perf_counter()
+    out["idx_perm"] = np.array(rec.perm, dtype=np.int32).reshape(n_perm, X.shape[0])
+    out["idx_boot"] = np.array(rec.boot, dtype=np.int32).reshape(n_boot, X.shape[0])
+    out["seconds"] = t2 - t0
+    out["rate"] = (n_perm + n_boot) / (t2 - t0)
+    out["desc"] = (f"{n_perm} permutations ({(t1 - t0) / max(n_perm, 1) * 1e3:.0f} ms each) + {n_boot} bootstraps "
+                   f"({(t2 - t1) / max(n_boot, 1) * 1e3:.0f} ms each) of the full-size workload through the unmodified "
+                   f"reference's ResampleTest._create (baseline/_ref/plspy 0.3.0, numpy "
+                   f"{np.__version__}, OPENBLAS/OMP threads = library default)")
+    return out
+
+
+def cpu_arm(X, groups, C, n_each, seed=7, analysis=None):
+    """(rate, seconds, description, kind, sample) of the CPU arm: the unmodified reference when baseline/_ref is
+    there, else the oracle port."""
+    if reference_available():
+        r = reference_sample(X, groups, C, n_each, n_each, seed=seed, analysis=analysis)
+        return r["rate"], r["seconds"], r["desc"], "reference", r
+    r = port_rate(X, groups, C, n_each, seed=seed)
+    return r["value"], r["seconds"], r["sample"], "port", None
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm (oracle port) on the host cores; rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     X = make_data(p=args.voxels)
     cores = blas_threads()
-    n_each = args.ref_sample
-    for _ in range(args.warmup):
-        cpu_reference_rate(X, GROUPS, C, 1)
-    rates, secs, desc = [], [], ""
+    n_each = args.ref_sample if args.ref_sample > 0 else 4
+    analysis, kind = None, "port"
+    for _ in range(min(args.warmup, 2)):
+        _, _, _, kind, r = cpu_arm(X, GROUPS, C, 1, analysis=analysis)
+        analysis = r["analysis"] if r is not None else None
+    units, secs, desc = [], [], ""
     for _ in range(args.steps):
-        r, dt, desc = cpu_reference_rate(X, GROUPS, C, n_each)
-        rates.append(2 * n_each); secs.append(dt)
-    value = sum(rates) / sum(secs)
+        _, dt, desc, kind, r = cpu_arm(X, GROUPS, C, n_each, analysis=analysis)
+        analysis = r["analysis"] if r is not None else None
+        units.append(2 * n_each); secs.append(dt)
+    value = sum(units) / sum(secs)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(GROUPS, C, args.voxels, NPERM, NBOOT),
                    "sample_per_step": f"{n_each} perm + {n_each} boot"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     args._quiet.restore()
     print(json.dumps(line), flush=True)
+
+
+def check_against_reference(ref, n_each, make_engine, Xd, bp, cf, co, precision):
+    """The GPU path on the n_each + n_each resamples the reference sample drew (full benchmark shape, the reference's
+    own U, s, V), compared field by field with the reference's results.  Tolerances of BASELINE.json: p-values exact,
+    singular values 1e-10 (exact mode), bootstrap ratios 1e-4."""
+    U, s, V, Tvsc = ref["analysis"]
+    live = np.abs(s) > 1e-8
+    out = {"against": "unmodified reference (baseline/_ref) on the same index vectors, full benchmark shape",
+           "n_perm": n_each, "n_boot": n_each, "precision_mode": precision}
+    eng = make_engine(Xd, precision)
+    rt = bp.ResampleTest._create("mct", Xd, None, U, s.copy(), V, co, MCTYPE, preprocess=cf._mean_centre, nperm=n_each,
+                                 nboot=n_each, Tvsc_orig=Tvsc, CI=0.95, perm_indices=ref["idx_perm"],
+                                 boot_indices=ref["idx_boot"], engine=eng)
+    rp, rb = ref["perm"], ref["boot"]
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+    out["p_values_equal"] = bool(np.array_equal(rt.permute_ratio, rp.permute_ratio))
+    out["stepdown_equal"] = bool(np.array_equal(rt.stepdown_ratio, rp.stepdown_ratio))
+    # the reference keeps only the last permutation's singular values (s_list[i:, ] = s_hat, :439-441)
+    out["perm_s_hat_max_rel"] = rel(rt.perm_debug_dict["s_list"][-1][live], rp.perm_debug_dict["s_list"][-1][live])
+    out["std_errs_max_rel"] = rel(rt.std_errs[:, live], rb.std_errs[:, live])
+    out["boot_ratios_max_rel"] = rel(rt.boot_ratios[:, live], rb.boot_ratios[:, live])
+    out["conf_ints_max_abs"] = float(max(np.max(np.abs(rt.conf_ints[i][:, live] - rb.conf_ints[i][:, live]))
+                                         for i in (0, 1)))
+    out["u_hat_max_abs"] = float(np.max(np.abs(rt.boot_debug_dict["left_sv_sampled"][:, :, live]
+                                               - rb.boot_debug_dict["left_sv_sampled"][:, :, live])))
+    tol_b = 1e-8 if precision == "fp64" else 1e-4
+    out["ok"] = bool(out["p_values_equal"] and out["stepdown_equal"] and out["perm_s_hat_max_rel"] < 1e-10
+                     and out["std_errs_max_rel"] < tol_b and out["boot_ratios_max_rel"] < tol_b)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -433,13 +554,20 @@ def run_gpu(args):
                 "tolerance": "north star: bootstrap ratios within 1e-4"},
         }
 
-    # ---- CPU baseline: bounded sample of the same workload on the host cores (N=1 only)
+    # ---- CPU baseline: bounded sample of the same workload on the host cores (N=1 only), and -- on exactly the
+    # resamples that sample drew -- the parity check of the GPU path against it at the benchmark shape
     cpu = None
+    check = {"permute_ratio_lv0": float(rt.permute_ratio[0]),
+             "boot_ratio_max": float(np.nanmax(np.abs(rt.boot_ratios[:, 0])))}
     if world == 1 and not args.no_cpu_baseline:
-        rate, dt, desc = cpu_reference_rate(X, GROUPS, C, args.ref_sample)
-        cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": desc,
-               "seconds": dt}
-
+        n_each = args.ref_sample if args.ref_sample > 0 else 10
+        rate, dt, desc, kind, ref = cpu_arm(X, GROUPS, C, n_each)
+        cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(), "kind": kind,
+               "sample": desc, "seconds": dt}
+        if ref is not None:
+            cpu["port"] = port_rate(X, GROUPS, C, max(2, n_each // 2))
+            check.update(check_against_reference(ref, n_each, lambda a, b: Engine(a, device=dev, precision=b), Xd, bp, cf,
+                                                 co, args.precision))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -455,7 +583,7 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "fast_mode": fast_mode,
         "step_ms": step_log,
-        "check": {"permute_ratio_lv0": float(rt.permute_ratio[0]), "boot_ratio_max": float(np.nanmax(np.abs(rt.boot_ratios[:, 0])))},
+        "check": check,
     }
     args._quiet.restore()
     print(json.dumps(line), flush=True)
@@ -495,7 +623,9 @@ def main():
     ap.add_argument("--voxels", type=int, default=P_VOX)
     ap.add_argument("--perms", type=int, default=NPERM)
     ap.add_argument("--boots", type=int, default=NBOOT)
-    ap.add_argument("--ref-sample", type=int, default=20, help="perms and boots per CPU-baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="perms and boots per CPU sample (0 = default: 10 in the cpu_baseline leg, 4 per step of "
+                         "--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32x3"],
                     help="fp64 = exact mode (headline); tf32x3 = fast mode only")

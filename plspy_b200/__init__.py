@@ -18,7 +18,10 @@ def __getattr__(name):
     if name in ("PLS", "methods"):
         from . import pls
         return getattr(pls, name)
-    if name in ("bootstrap_permutation", "class_functions", "pls", "pls_classes", "resample",
+    if name in ("install", "uninstall"):
+        from . import plugin
+        return getattr(plugin, name)
+    if name in ("plugin", "bootstrap_permutation", "class_functions", "pls", "pls_classes", "resample",
                 "split_half_resampling", "engine", "dist", "build", "_lib"):
         import importlib
         return importlib.import_module("." + name, __name__)
