@@ -311,7 +311,7 @@ def run_reference(args):
         return
     X = make_data(p=args.voxels)
     cores = blas_threads()
-    n_each = args.ref_sample if args.ref_sample > 0 else 4
+    n_each = args.ref_sample if args.ref_sample > 0 else 5
     analysis, kind = None, "port"
     for _ in range(min(args.warmup, 2)):
         _, _, _, kind, r = cpu_arm(X, GROUPS, C, 1, analysis=analysis)
@@ -370,6 +370,54 @@ def check_against_reference(ref, n_each, make_engine, Xd, bp, cf, co, precision)
     return out
 
 
+def phase_timeline(run, torch):
+    """One pass of `run()` with every Engine call and every collective bracketed by CUDA events and host time stamps
+    (after one untimed pass with the wrappers in place).  Returns {"wall_ms", "phases": {name: {n, gpu_ms, host_ms}},
+    "timeline": [[name, host_start_ms, host_end_ms, gpu_ms], ...]} -- where one step of the (sharded) job spends its
+    time on this rank."""
+    from plspy_b200 import dist as pdist
+    from plspy_b200.engine import Engine
+    log, saved = [], []
+
+    def wrap(owner, name):
+        fn = getattr(owner, name)
+        saved.append((owner, name, fn))
+
+        def w(*a, **k):
+            h0 = time.perf_counter()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(*a, **k); e1.record()
+            log.append((name, h0, time.perf_counter(), e0, e1))
+            return out
+        setattr(owner, name, w)
+    for name in ("gram_of", "gram_collective", "xv", "nspace", "perm_count", "uhat", "boot_moments", "boot_finalize",
+                 "colstd", "to_host_async", "_upload_x"):
+        wrap(Engine, name)
+    for name in ("allreduce_sum_", "allreduce_packed_", "gather_rows"):
+        wrap(pdist, name)
+    try:
+        run(); torch.cuda.synchronize(); log.clear()
+        if pdist.world()[1] > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); run(); torch.cuda.synchronize(); t1 = time.perf_counter()
+    finally:
+        for owner, name, fn in saved:
+            setattr(owner, name, fn)
+    agg, tl = {}, []
+    for name, h0, h1, e0, e1 in log:
+        g = e0.elapsed_time(e1)
+        d = agg.setdefault(name, {"n": 0, "gpu_ms": 0.0, "host_ms": 0.0})
+        d["n"] += 1; d["gpu_ms"] += g; d["host_ms"] += 1e3 * (h1 - h0)
+        tl.append([name, round(1e3 * (h0 - t0), 3), round(1e3 * (h1 - t0), 3), round(g, 3)])
+    for d in agg.values():
+        d["gpu_ms"] = round(d["gpu_ms"], 3); d["host_ms"] = round(d["host_ms"], 3)
+    return {"wall_ms": round(1e3 * (t1 - t0), 3), "phases": agg, "timeline": tl,
+            "note": "gpu_ms of nested calls (gram_of inside gram_collective, to_device inside others) overlap; "
+                    "to_host_async gpu_ms covers only the enqueue of the copies"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -412,17 +460,27 @@ def run_gpu(args):
     Xh = torch.from_numpy(X).pin_memory(); Vh = torch.from_numpy(np.ascontiguousarray(V)).pin_memory()
     gph = torch.from_numpy(gp).pin_memory(); gbh = torch.from_numpy(gb).pin_memory()
     Xd, Vd, gpd, gbd = Xh.to(dev), Vh.to(dev), gph.to(dev), gbh.to(dev)
+    # job = (total permutations, total bootstraps, index matrices pinned / resident)
+    jobs = {"weak": (nperm * world, nboot * world, gph, gbh, gpd, gbd)}
+    if world > 1:
+        # strong scaling: the SAME fixed job as the N = 1 run (nperm + nboot in total, identical index matrices on
+        # every rank), sharded over the ranks
+        np.random.seed(1234 + 3)
+        sp = torch.from_numpy(resample.permutation_indices("mct", nperm, co)[0].astype(np.int32)).pin_memory()
+        sb = torch.from_numpy(resample.bootstrap_indices("mct", nboot, co)[0].astype(np.int32)).pin_memory()
+        jobs["strong"] = (nperm, nboot, sp, sb, sp.to(dev), sb.to(dev))
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
 
-    def one_pass(Xa, Va, pa, ba, events=None, precision="fp64"):
+    def one_pass(Xa, Va, pa, ba, events=None, precision="fp64", totals=None):
         eng = Engine(Xa, device=dev, precision=precision)            # Gram (and TF32 planes) recomputed every step
         eng.kernel_events = events
         if events is not None and sampler is not None:
             eng.on_mark = sampler.on_mark
+        tp, tb = totals if totals is not None else (nperm * world, nboot * world)
         rt = bp.ResampleTest._create("mct", Xa, None, U, s.copy(), Va, co, MCTYPE, preprocess=cf._mean_centre,
-                                     nperm=nperm * world, nboot=nboot * world, Tvsc_orig=Tvsc, CI=0.95,
+                                     nperm=tp, nboot=tb, Tvsc_orig=Tvsc, CI=0.95,
                                      perm_indices=pa, boot_indices=ba, engine=eng)
         return eng, rt
 
@@ -433,39 +491,47 @@ def run_gpu(args):
 
     step_log = {}
 
-    def timed(fn, steps, tag=None):
-        sync_all()
+    def timed(fn, steps, tag=None, collective=True):
+        coll = collective and world > 1
+        if coll:
+            dist.barrier()
+        torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         evs[0].record()
         for i in range(steps):
             fn()
             evs[i + 1].record()
-        sync_all()
+        if coll:
+            dist.barrier()
+        torch.cuda.synchronize()
         if tag is not None:
             step_log[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 3) for i in range(steps)]
         ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device=dev, dtype=torch.float64)
-        if world > 1:
+        if coll:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def measure(precision):
+    def measure(precision, job="weak"):
         """value arm (inputs resident in HBM) and e2e arm (pinned host buffers in, host results out) for one
-        precision mode; returns a dict of raw timings."""
+        precision mode and one job; returns a dict of raw timings."""
+        tp, tb, gph, gbh, gpd, gbd = jobs[job]
+        tag = "" if job == "weak" else job + "_"
+        one = lambda *a, **k: one_pass(*a, totals=(tp, tb), **k)       # noqa: E731
         # warm-up with the same object-retention pattern as the timed loop (the previous engine stays alive until
         # the next pass has finished), so that torch's caching allocators reach their steady state -- two sets
         # of blocks -- before the timed region; otherwise the second timed step pays a one-off 10-50 ms for
         # fresh device / pinned allocations
         keep = {}
         for _ in range(max(args.warmup, 3)):
-            keep["eng"] = one_pass(Xd, Vd, gpd, gbd, {}, precision)[0]
+            keep["eng"] = one(Xd, Vd, gpd, gbd, {}, precision)[0]
         events = {}
         launches0 = _lib.launch_count()
         if sampler is not None:
             sampler.begin()
         # (only the last engine is kept alive: retaining all of them makes every step allocate fresh device memory,
         # and driver allocations that collide with the clock sampler's NVML queries stall for tens of ms)
-        total_ms = timed(lambda: keep.__setitem__("eng", one_pass(Xd, Vd, gpd, gbd, events, precision)[0]), args.steps,
-                         f"value_{precision}")
+        total_ms = timed(lambda: keep.__setitem__("eng", one(Xd, Vd, gpd, gbd, events, precision)[0]), args.steps,
+                         f"{tag}value_{precision}")
         clocks = sampler.end() if sampler is not None else None
         launches = _lib.launch_count() - launches0
         kms = keep["eng"].kernel_ms("boot_moments") if keep else []
@@ -475,10 +541,10 @@ def run_gpu(args):
         def e2e_step():
             # X, V and the index matrices start in pinned host memory; the engine uploads X and V and, of the
             # global index matrices, only the rows of this rank's shard
-            last["rt"] = one_pass(Xh, Vh, gph, gbh, precision=precision)[1]
+            last["rt"] = one(Xh, Vh, gph, gbh, precision=precision)[1]
         for _ in range(2):
             e2e_step()
-        e2e_ms = timed(e2e_step, args.steps, f"e2e_{precision}") / args.steps
+        e2e_ms = timed(e2e_step, args.steps, f"{tag}e2e_{precision}") / args.steps
         return {"ms_step": total_ms / args.steps, "kern_ms": sum(kms) / len(kms) if kms else float("nan"),
                 "launches": launches, "clocks": clocks, "e2e_ms": e2e_ms, "rt": last["rt"]}
 
@@ -489,6 +555,46 @@ def run_gpu(args):
     fast = measure("tf32x3") if (args.precision == "fp64" and not args.no_fast_mode) else None
     ms_step, kern_ms, launches, clocks, e2e_ms, rt = (main[k] for k in ("ms_step", "kern_ms", "launches", "clocks",
                                                                         "e2e_ms", "rt"))
+    # ---- strong scaling (N > 1): the fixed N = 1 job sharded over the ranks, next to the same job on rank 0 alone
+    strong = None
+    if world > 1 and not args.no_strong:
+        from plspy_b200 import dist as pdist
+        modes = [args.precision] + (["tf32x3"] if fast is not None else [])
+        sm = {m: measure(m, "strong") for m in modes}
+        tp, tb, sph, sbh, spd, sbd = jobs["strong"]
+        ph = {m: phase_timeline(lambda m=m: one_pass(Xd, Vd, spd, sbd, None, m, totals=(tp, tb)), torch) for m in modes}
+        solo = {}
+        if rank == 0:
+            with pdist.local_only():
+                for m in modes:
+                    keep = {}
+                    for _ in range(3):
+                        keep["e"] = one_pass(Xd, Vd, spd, sbd, {}, m, totals=(tp, tb))[0]
+                    v = timed(lambda: keep.__setitem__("e", one_pass(Xd, Vd, spd, sbd, {}, m, totals=(tp, tb))[0]),
+                              args.steps, f"solo_value_{m}", collective=False) / args.steps
+                    keep.clear()
+                    for _ in range(2):
+                        one_pass(Xh, Vh, sph, sbh, precision=m, totals=(tp, tb))
+                    e = timed(lambda: one_pass(Xh, Vh, sph, sbh, precision=m, totals=(tp, tb)), args.steps,
+                              f"solo_e2e_{m}", collective=False) / args.steps
+                    solo[m] = (v, e)
+        dist.barrier()
+        if rank == 0:
+            strong = {"workload": workload_name(GROUPS, C, p, nperm, nboot).replace(" per GPU", " IN TOTAL, sharded over "
+                                                                                      f"{world} GPUs"),
+                      "scaling": "strong", "n_gpus": world}
+            for m in modes:
+                t1v, t1e = solo[m]
+                rec = {"value": (tp + tb) / (sm[m]["ms_step"] * 1e-3), "unit": UNIT, "ms_per_step": sm[m]["ms_step"],
+                       "e2e": {"value": (tp + tb) / (sm[m]["e2e_ms"] * 1e-3), "unit": UNIT,
+                               "ms_per_step": sm[m]["e2e_ms"]},
+                       "kernel_ms": sm[m]["kern_ms"],
+                       "same_job_on_one_gpu": {"ms_per_step": t1v, "e2e_ms_per_step": t1e,
+                                               "how": "rank 0 alone, same process, other ranks idle"},
+                       "efficiency": t1v / (world * sm[m]["ms_step"]),
+                       "e2e_efficiency": t1e / (world * sm[m]["e2e_ms"]),
+                       "phase_timeline_rank0": ph[m]}
+                strong["exact" if m == "fp64" else "fast"] = rec
     value = units_step / (ms_step * 1e-3)
     d2h = (rt.std_errs.nbytes + rt.boot_ratios.nbytes + rt.conf_ints[0].nbytes * 2 + rt.permute_ratio.nbytes * 2
            + rt.perm_debug_dict["s_list"].nbytes)
@@ -560,7 +666,7 @@ def run_gpu(args):
     check = {"permute_ratio_lv0": float(rt.permute_ratio[0]),
              "boot_ratio_max": float(np.nanmax(np.abs(rt.boot_ratios[:, 0])))}
     if world == 1 and not args.no_cpu_baseline:
-        n_each = args.ref_sample if args.ref_sample > 0 else 10
+        n_each = args.ref_sample if args.ref_sample > 0 else 20
         rate, dt, desc, kind, ref = cpu_arm(X, GROUPS, C, n_each)
         cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(), "kind": kind,
                "sample": desc, "seconds": dt}
@@ -582,6 +688,7 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "fast_mode": fast_mode,
+        "strong": strong,
         "step_ms": step_log,
         "check": check,
     }
@@ -624,12 +731,13 @@ def main():
     ap.add_argument("--perms", type=int, default=NPERM)
     ap.add_argument("--boots", type=int, default=NBOOT)
     ap.add_argument("--ref-sample", type=int, default=0,
-                    help="perms and boots per CPU sample (0 = default: 10 in the cpu_baseline leg, 4 per step of "
+                    help="perms and boots per CPU sample (0 = default: 20 in the cpu_baseline leg, 5 per step of "
                          "--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32x3"],
                     help="fp64 = exact mode (headline); tf32x3 = fast mode only")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra fast-mode measurement")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling side record")
     args = ap.parse_args()
     with _QuietStdout() as quiet:
         args._quiet = quiet

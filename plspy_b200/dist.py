@@ -6,9 +6,29 @@ the same code runs under gloo on CPU tensors for the host-logic tests).
 import torch
 
 
+_LOCAL_ONLY = False
+
+
+class local_only:
+    """Context manager: inside it this process behaves as a single-process run (no shards, no collectives) even though
+    a process group exists -- e.g. rank 0 timing the whole job on its own GPU next to the sharded run (bench.py)."""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        self._prev, _LOCAL_ONLY = _LOCAL_ONLY, True
+        return self
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY = self._prev
+        return False
+
+
 def world():
     """(rank, world_size) of the default process group, (0, 1) when not initialised."""
     import torch.distributed as dist
+    if _LOCAL_ONLY:
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
