@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PLSB200_ABI_VERSION 1
+#define PLSB200_ABI_VERSION 2
 
 #define PLSB200_OK 0
 #define PLSB200_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */
@@ -231,12 +231,15 @@ int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin, int64_t p,
                               const int32_t* segs, int nseg, int nq, int nmax, int K, int s0, int ns, double* S3,
                               void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- K3: batched symmetric eigensolver, one warp per K x K matrix (K <= 32), one-sided Jacobi with
- * shuffle-based rotations.  Replaces np.linalg.svd of the K x p half-sample cross-block matrices
- * (class_functions.py:122 as called from split_half_resampling.py:194,207,255,311,612-613,...) through
- * their K x K Gram matrices.  A: B x K x K symmetric PSD.  evals: B x K descending.
- * evecs: B x K x K row-major, eigenvectors in COLUMNS.                                              */
-int plsb200_sym_eig_f64(const double* A, int K, int B, double* evals, double* evecs, void* stream);
+/* ---- K3: batched symmetric eigensolver, one-sided (Hestenes) Jacobi.  K <= 32: one warp per K x K matrix, columns
+ * in registers, shuffle-based rotations.  32 < K <= 112: one CTA per matrix, columns in shared memory, the K/2
+ * disjoint pairs of a tournament round rotated by K/2 warps in parallel.  Replaces np.linalg.svd of the K x p
+ * half-sample cross-block matrices (class_functions.py:122 as called from
+ * split_half_resampling.py:194,207,255,311,612-613,...) through their K x K Gram matrices.
+ * A: B x K x K symmetric PSD.  evals: B x K descending.  evecs: B x K x K row-major, eigenvectors in COLUMNS.
+ * status (B int32, may be NULL): 0 = converged, 1 = sweep limit reached (results must not be used).
+ * K > 112: PLSB200_EUNSUPPORTED.                                                                      */
+int plsb200_sym_eig_f64(const double* A, int K, int B, double* evals, double* evecs, int32_t* status, void* stream);
 
 /* ---- Gram blocks of S split-half resamples through G (task methods).
  * Half h of split s consists of the rows idx_h[s, 0..n_h) of X (null splits: rows of the permuted X,
@@ -247,7 +250,7 @@ int plsb200_split_gram_f64(const double* G, int N, const int32_t* idx1, int n1, 
                            int S, const double* A1, const double* A2, int K, double* S11, double* S12,
                            double* S22, void* stream);
 
-/* ---- split-half outputs from the Gram blocks (SVD methods; K <= 32).  With S11 = U1 diag(s1^2) U1^T,
+/* ---- split-half outputs from the Gram blocks (SVD methods; K <= 112).  With S11 = U1 diag(s1^2) U1^T,
  * S22 = U2 diag(s2^2) U2^T (singular values descending):
  *   s_train (S x K)     = s1                                   (split_half_resampling.py:195)
  *   s_test  (S x K x K) = V1^T M2^T U1 = diag(1/s1) U1^T S12 U1 (:196)
@@ -256,10 +259,13 @@ int plsb200_split_gram_f64(const double* G, int N, const int32_t* idx1, int n1, 
  *   s2      (S x K)     = s2
  * Any output pointer may be NULL.  Rows/columns belonging to zero singular values are written as 0
  * (LAPACK returns an arbitrary orthonormal completion there).  Signs of singular vectors are not
- * those of LAPACK: compare up to the sign of each latent variable.                                 */
+ * those of LAPACK: compare up to the sign of each latent variable.
+ * status (S int32, may be NULL): 1 where one of the two eigensolves of split s did not converge.
+ * K > 32 needs a workspace of plsb200_split_svd_f64_workspace(K, S) bytes (the eigenpairs of S11 and S22).  */
+size_t plsb200_split_svd_f64_workspace(int K, int S);
 int plsb200_split_svd_f64(const double* S11, const double* S12, const double* S22, int K, int S,
                           double* s_train, double* s_test, double* u_repro, double* v_repro, double* s2,
-                          void* stream);
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-side resampling index generator (no GPU work) -------------------------------------------------
  * Continues numpy's legacy global MT19937 stream -- `key` = the 624 state words, `*pos` = the position, both as

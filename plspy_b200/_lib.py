@@ -68,11 +68,12 @@ SIGNATURES = {
     "plsb200_boot_finalize_f64": (c_int, [c_double_p, c_double_p, c_int64, c_int, c_int64, c_double_p,
                                           c_double_p, c_double_p, c_void_p]),
     "plsb200_colstd_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_void_p]),
-    "plsb200_sym_eig_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_void_p]),
+    "plsb200_sym_eig_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_void_p, c_void_p]),
     "plsb200_split_gram_f64": (c_int, [c_double_p, c_int, c_int32_p, c_int, c_int32_p, c_int, c_int, c_double_p,
                                        c_double_p, c_int, c_double_p, c_double_p, c_double_p, c_void_p]),
+    "plsb200_split_svd_f64_workspace": (c_size_t, [c_int, c_int]),
     "plsb200_split_svd_f64": (c_int, [c_double_p, c_double_p, c_double_p, c_int, c_int, c_double_p, c_double_p,
-                                      c_double_p, c_double_p, c_double_p, c_void_p]),
+                                      c_double_p, c_double_p, c_double_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_cell_standardize_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_int32_p, c_int, c_double_p,
                                              c_double_p, c_void_p]),
     "plsb200_nspace_coef_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int, c_double_p, c_int, c_double_p,
@@ -109,8 +110,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.restype = _res
     _f.argtypes = _args
 
-if lib.plsb200_abi_version() != 1:
-    raise ImportError(f"{LIB_PATH}: ABI version {lib.plsb200_abi_version()} != 1; rebuild")
+ABI_VERSION = 2
+if lib.plsb200_abi_version() != ABI_VERSION:
+    raise ImportError(f"{LIB_PATH}: ABI version {lib.plsb200_abi_version()} != {ABI_VERSION}; rebuild")
 
 
 def check(rc, what):

@@ -18,16 +18,23 @@
 namespace plsb {
 
 // ------------------------------------------------------------------------------------------------
+// Sweep limit of both Jacobi solvers.  Cyclic one-sided Jacobi converges quadratically; the K x K Gram blocks of this
+// path need 6-10 sweeps.  A matrix that has not converged within the limit is reported through the `status` output
+// of the entry points (1 = not converged) and the Python layer raises -- results are never consumed unchecked.
+constexpr int JACOBI_MAX_SWEEPS = 60;
+
 // One-sided (Hestenes) Jacobi on a symmetric PSD matrix, one warp per matrix.  Lane j owns column j
 // of W (initially A) and of V (initially I); in each of the n-1 steps of a round-robin tournament
 // every lane fetches its partner's columns with shuffles and both lanes of a pair apply the same
 // plane rotation, so n/2 rotations run in parallel.  On exit W = A V has orthogonal columns:
 // eigenvalue_j = ||w_j||, eigenvector_j = v_j.  Returns the rank (0 = largest) of this lane's pair.
 template <int KM>
-__device__ __forceinline__ int jacobi_warp(double (&w)[KM], double (&v)[KM], double& lambda, int lane) {
+__device__ __forceinline__ int jacobi_warp(double (&w)[KM], double (&v)[KM], double& lambda, int lane,
+                                           bool& converged) {
     constexpr int n = KM;          // even
     const double tol = 4.0 * DBL_EPSILON;
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    converged = false;
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
         bool rotated = false;
 #pragma unroll 1
         for (int r = 0; r < n - 1; ++r) {
@@ -71,7 +78,7 @@ __device__ __forceinline__ int jacobi_warp(double (&w)[KM], double (&v)[KM], dou
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, rotated)) break;
+        if (!__any_sync(0xffffffffu, rotated)) { converged = true; break; }
     }
     double nn = 0.0;
 #pragma unroll
@@ -97,17 +104,181 @@ __device__ __forceinline__ void load_cols(const double* A, int K, int lane, doub
 
 template <int KM>
 __global__ void __launch_bounds__(128) sym_eig_kernel(const double* __restrict__ A, int K, int B,
-                                                     double* __restrict__ evals, double* __restrict__ evecs) {
+                                                     double* __restrict__ evals, double* __restrict__ evecs,
+                                                     int32_t* __restrict__ status) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double w[KM], v[KM], lam;
+    bool conv;
     load_cols<KM>(A + (size_t)warp * K * K, K, lane, w, v);
-    const int rank = jacobi_warp<KM>(w, v, lam, lane);
+    const int rank = jacobi_warp<KM>(w, v, lam, lane, conv);
+    if (status && lane == 0 && !conv) status[warp] = 1;          // raised only: the entry point zeroes the array
     if (lane < KM && rank < K) {
         evals[(size_t)warp * K + rank] = lam;
 #pragma unroll
         for (int e = 0; e < KM; ++e)
             if (e < K) evecs[((size_t)warp * K + e) * K + rank] = v[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same one-sided Jacobi for 32 < K <= JACOBI_CTA_KMAX, one CTA per matrix: the columns of W and V live in shared
+// memory (column-major), the n/2 disjoint column pairs of a tournament round are rotated by n/2 warps in parallel
+// (lanes stride the column, dot products by xor-shuffles), one __syncthreads per round.  Same rotation formula,
+// threshold and ordering of the eigenpairs as jacobi_warp.  (behaviour designs: K = groups x conditions x behaviours,
+// e.g. 3 x 4 x 4 = 48; multiblock: groups x (conditions + |bscan| x behaviours).)
+constexpr int JACOBI_CTA_KMAX = 112;       // 2 n^2 doubles of shared memory: 196 KB at n = 112
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+__global__ void __launch_bounds__(1024) sym_eig_cta_kernel(const double* __restrict__ A, int K, int B,
+                                                          double* __restrict__ evals, double* __restrict__ evecs,
+                                                          int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) double smj[];
+    const int n = (K + 1) & ~1;
+    double* W = smj;                       // [n][n]: column c at W + c*n
+    double* V = W + (size_t)n * n;
+    double* lam = V + (size_t)n * n;       // [n]
+    __shared__ int any_rot;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const double tol = 4.0 * DBL_EPSILON;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * K * K;
+        for (int i = tid; i < n * n; i += nt) {
+            const int c = i / n, e = i % n;
+            W[i] = (c < K && e < K) ? Ab[(size_t)e * K + c] : 0.0;
+            V[i] = (c == e) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        bool conv = false;
+        for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && !conv; ++sweep) {
+            if (tid == 0) any_rot = 0;
+            __syncthreads();
+            for (int r = 0; r < n - 1; ++r) {
+                for (int q = warp; q < n / 2; q += nw) {
+                    int i, j;
+                    if (q == 0) { i = r; j = n - 1; }
+                    else {
+                        i = (r + q) % (n - 1);
+                        j = (r - q + (n - 1)) % (n - 1);
+                        if (i > j) { const int t = i; i = j; j = t; }
+                    }
+                    double* wi = W + (size_t)i * n; double* wj = W + (size_t)j * n;
+                    double alpha = 0.0, beta = 0.0, gam = 0.0;
+                    for (int e = lane; e < n; e += 32) {
+                        const double a = wi[e], c = wj[e];
+                        alpha = fma(a, a, alpha); beta = fma(c, c, beta); gam = fma(a, c, gam);
+                    }
+                    alpha = warp_sum(alpha); beta = warp_sum(beta); gam = warp_sum(gam);
+                    if (gam != 0.0 && fabs(gam) > tol * sqrt(alpha * beta)) {
+                        const double zeta = (beta - alpha) / (2.0 * gam);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                        double* vi = V + (size_t)i * n; double* vj = V + (size_t)j * n;
+                        for (int e = lane; e < n; e += 32) {      // w_i <- c w_i - s w_j ; w_j <- s w_i + c w_j
+                            const double a = wi[e], d = wj[e];
+                            wi[e] = fma(-sn, d, c * a); wj[e] = fma(sn, a, c * d);
+                            const double x = vi[e], y = vj[e];
+                            vi[e] = fma(-sn, y, c * x); vj[e] = fma(sn, x, c * y);
+                        }
+                        if (lane == 0) any_rot = 1;
+                    }
+                }
+                __syncthreads();
+            }
+            conv = any_rot == 0;
+            __syncthreads();
+        }
+        if (status && tid == 0 && !conv) status[b] = 1;              // raised only
+        for (int c = warp; c < n; c += nw) {
+            double nn = 0.0;
+            for (int e = lane; e < n; e += 32) nn = fma(W[(size_t)c * n + e], W[(size_t)c * n + e], nn);
+            nn = warp_sum(nn);
+            if (lane == 0) lam[c] = sqrt(nn);
+        }
+        __syncthreads();
+        for (int c = warp; c < n; c += nw) {
+            const double l = lam[c];
+            int rank = 0;
+            for (int o = lane; o < n; o += 32) {
+                const double x = lam[o];
+                if (x > l || (x == l && o < c)) ++rank;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+            if (rank < K) {
+                if (lane == 0) evals[(size_t)b * K + rank] = l;
+                for (int e = lane; e < K; e += 32) evecs[((size_t)b * K + e) * K + rank] = V[(size_t)c * n + e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int launch_sym_eig_cta(const double* A, int K, int B, double* evals, double* evecs, int32_t* status,
+                              cudaStream_t st) {
+    const int n = (K + 1) & ~1;
+    const size_t smem = ((size_t)2 * n * n + n) * sizeof(double);
+    PLSB_CUDA(cudaFuncSetAttribute(sym_eig_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int warps = n / 2; if (warps > 32) warps = 32;
+    const int grid = B < 4 * num_sms() ? B : 4 * num_sms();
+    sym_eig_cta_kernel<<<grid, warps * 32, smem, st>>>(A, K, B, evals, evecs, status);
+    PLSB_LAUNCH_CHECK("sym_eig_cta_kernel");
+    return PLSB200_OK;
+}
+
+// K x K outputs of a split from the eigenpairs of S11 and S22 (the K > 32 path of plsb200_split_svd_f64):
+// lam_h = eigenvalues of S_hh (= squared singular values), U_h = eigenvectors in columns (row-major K x K).
+__global__ void __launch_bounds__(256) split_out_kernel(const double* __restrict__ S12, const double* __restrict__ lam1,
+                                                       const double* __restrict__ U1, const double* __restrict__ lam2,
+                                                       const double* __restrict__ U2, int K,
+                                                       double* __restrict__ s_train, double* __restrict__ s_test,
+                                                       double* __restrict__ u_repro, double* __restrict__ v_repro,
+                                                       double* __restrict__ s2_out) {
+    extern __shared__ __align__(16) double smo[];
+    double* P = smo;                      // [K][K]
+    double* sv1 = P + (size_t)K * K; double* sv2 = sv1 + K;
+    const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* C = S12 + (size_t)s * K * K;
+    const double* Ua = U1 + (size_t)s * K * K; const double* Ub = U2 + (size_t)s * K * K;
+    for (int k = tid; k < K; k += nt) {
+        sv1[k] = sqrt(fmax(lam1[(size_t)s * K + k], 0.0));      // singular value of M_h = sqrt(eigenvalue of S_hh)
+        sv2[k] = sqrt(fmax(lam2[(size_t)s * K + k], 0.0));
+    }
+    __syncthreads();
+    if (s_train) for (int k = tid; k < K; k += nt) s_train[(size_t)s * K + k] = sv1[k];
+    if (s2_out) for (int k = tid; k < K; k += nt) s2_out[(size_t)s * K + k] = sv2[k];
+    if (v_repro)
+        for (int o = tid; o < K * K; o += nt) {
+            const int i = o / K, j = o % K;
+            double acc = 0.0;
+            for (int r = 0; r < K; ++r) acc = fma(Ua[(size_t)r * K + i], Ub[(size_t)r * K + j], acc);
+            v_repro[(size_t)s * K * K + o] = acc;
+        }
+    for (int pass = 0; pass < 2; ++pass) {
+        double* out = pass == 0 ? s_test : u_repro;
+        if (!out) continue;
+        const double* Uh = pass == 0 ? Ua : Ub;
+        __syncthreads();
+        for (int o = tid; o < K * K; o += nt) {
+            const int r = o / K, j = o % K;
+            double acc = 0.0;
+            for (int c = 0; c < K; ++c) acc = fma(C[(size_t)r * K + c], Uh[(size_t)c * K + j], acc);
+            P[o] = acc;
+        }
+        __syncthreads();
+        for (int o = tid; o < K * K; o += nt) {
+            const int i = o / K, j = o % K;
+            double acc = 0.0;
+            for (int r = 0; r < K; ++r) acc = fma(Ua[(size_t)r * K + i], P[(size_t)r * K + j], acc);
+            double scale = sv1[i] > 0.0 ? 1.0 / sv1[i] : 0.0;
+            if (pass == 1) scale *= sv2[j] > 0.0 ? 1.0 / sv2[j] : 0.0;
+            out[(size_t)s * K * K + o] = acc * scale;
+        }
     }
 }
 
@@ -178,7 +349,7 @@ __global__ void __launch_bounds__(64) split_svd_kernel(const double* __restrict_
                                                       const double* __restrict__ S22, int K,
                                                       double* __restrict__ s_train, double* __restrict__ s_test,
                                                       double* __restrict__ u_repro, double* __restrict__ v_repro,
-                                                      double* __restrict__ s2_out) {
+                                                      double* __restrict__ s2_out, int32_t* __restrict__ status) {
     __shared__ double U[2][KM * KM];      // eigenvectors as columns, sorted: U[h][r*KM + c]
     __shared__ double sv[2][KM];          // singular values sqrt(lambda)
     __shared__ double P[KM * KM];         // S12 . U1 or S12 . U2
@@ -186,8 +357,10 @@ __global__ void __launch_bounds__(64) split_svd_kernel(const double* __restrict_
     {
         const double* A = (warp == 0 ? S11 : S22) + (size_t)s * K * K;
         double w[KM], v[KM], lam;
+        bool conv;
         load_cols<KM>(A, K, lane, w, v);
-        const int rank = jacobi_warp<KM>(w, v, lam, lane);
+        const int rank = jacobi_warp<KM>(w, v, lam, lane, conv);
+        if (status && lane == 0 && !conv) atomicOr(status + s, 1);
         if (lane < KM && rank < K) {
             sv[warp][rank] = sqrt(lam);
 #pragma unroll
@@ -236,20 +409,24 @@ __global__ void __launch_bounds__(64) split_svd_kernel(const double* __restrict_
 
 using namespace plsb;
 
-extern "C" int plsb200_sym_eig_f64(const double* A, int K, int B, double* evals, double* evecs, void* stream) {
+extern "C" int plsb200_sym_eig_f64(const double* A, int K, int B, double* evals, double* evecs, int32_t* status,
+                                   void* stream) {
     PLSB_CHECK_ARG(A && evals && evecs, "sym_eig_f64: null pointer");
     PLSB_CHECK_ARG(K > 0 && B >= 0, "sym_eig_f64: bad shape");
-    if (K > 32) {
-        set_err("sym_eig_f64: K=%d > 32 not supported by the warp-per-matrix solver", K);
+    if (K > JACOBI_CTA_KMAX) {
+        set_err("sym_eig_f64: K=%d > %d not supported (columns of W and V must fit in shared memory)", K,
+                JACOBI_CTA_KMAX);
         return PLSB200_EUNSUPPORTED;
     }
     if (B == 0) return PLSB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (status) PLSB_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), st));
+    if (K > 32) return launch_sym_eig_cta(A, K, B, evals, evecs, status, st);
     const int grid = (int)cdiv((int64_t)B * 32, 128);
-    if (K <= 8) sym_eig_kernel<8><<<grid, 128, 0, st>>>(A, K, B, evals, evecs);
-    else if (K <= 16) sym_eig_kernel<16><<<grid, 128, 0, st>>>(A, K, B, evals, evecs);
-    else if (K <= 24) sym_eig_kernel<24><<<grid, 128, 0, st>>>(A, K, B, evals, evecs);
-    else sym_eig_kernel<32><<<grid, 128, 0, st>>>(A, K, B, evals, evecs);
+    if (K <= 8) sym_eig_kernel<8><<<grid, 128, 0, st>>>(A, K, B, evals, evecs, status);
+    else if (K <= 16) sym_eig_kernel<16><<<grid, 128, 0, st>>>(A, K, B, evals, evecs, status);
+    else if (K <= 24) sym_eig_kernel<24><<<grid, 128, 0, st>>>(A, K, B, evals, evecs, status);
+    else sym_eig_kernel<32><<<grid, 128, 0, st>>>(A, K, B, evals, evecs, status);
     PLSB_LAUNCH_CHECK("sym_eig_kernel");
     return PLSB200_OK;
 }
@@ -274,21 +451,48 @@ extern "C" int plsb200_split_gram_f64(const double* G, int N, const int32_t* idx
     return PLSB200_OK;
 }
 
+extern "C" size_t plsb200_split_svd_f64_workspace(int K, int S) {
+    if (K <= 32 || S <= 0) return 16;
+    return (size_t)2 * S * ((size_t)K * K + K) * sizeof(double);      // eigenpairs of S11 and S22
+}
+
 extern "C" int plsb200_split_svd_f64(const double* S11, const double* S12, const double* S22, int K, int S,
                                      double* s_train, double* s_test, double* u_repro, double* v_repro, double* s2,
-                                     void* stream) {
+                                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     PLSB_CHECK_ARG(S11 && S12 && S22, "split_svd_f64: null pointer");
     PLSB_CHECK_ARG(K > 0 && S >= 0, "split_svd_f64: bad shape");
-    if (K > 32) {
-        set_err("split_svd_f64: K=%d > 32 not supported", K);
+    if (K > JACOBI_CTA_KMAX) {
+        set_err("split_svd_f64: K=%d > %d not supported", K, JACOBI_CTA_KMAX);
         return PLSB200_EUNSUPPORTED;
     }
     if (S == 0) return PLSB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (K <= 8) split_svd_kernel<8><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2);
-    else if (K <= 16) split_svd_kernel<16><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2);
-    else if (K <= 24) split_svd_kernel<24><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2);
-    else split_svd_kernel<32><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2);
+    if (status) PLSB_CUDA(cudaMemsetAsync(status, 0, (size_t)S * sizeof(int32_t), st));
+    if (K > 32) {
+        // CTA-per-matrix eigensolver on S11 and S22, then the outputs from the eigenpairs
+        if (!workspace || workspace_bytes < plsb200_split_svd_f64_workspace(K, S)) {
+            set_err("split_svd_f64: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                    plsb200_split_svd_f64_workspace(K, S));
+            return PLSB200_EWORKSPACE;
+        }
+        double* U1 = static_cast<double*>(workspace);
+        double* U2 = U1 + (size_t)S * K * K;
+        double* l1 = U2 + (size_t)S * K * K;
+        double* l2 = l1 + (size_t)S * K;
+        int rc = launch_sym_eig_cta(S11, K, S, l1, U1, status, st);      // status[s] is only ever raised to 1,
+        if (rc) return rc;                                               // so both solves report into it
+        rc = launch_sym_eig_cta(S22, K, S, l2, U2, status, st);
+        if (rc) return rc;
+        const size_t smem = ((size_t)K * K + 2 * K) * sizeof(double);
+        PLSB_CUDA(cudaFuncSetAttribute(split_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        split_out_kernel<<<S, 256, smem, st>>>(S12, l1, U1, l2, U2, K, s_train, s_test, u_repro, v_repro, s2);
+        PLSB_LAUNCH_CHECK("split_out_kernel");
+        return PLSB200_OK;
+    }
+    if (K <= 8) split_svd_kernel<8><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2, status);
+    else if (K <= 16) split_svd_kernel<16><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2, status);
+    else if (K <= 24) split_svd_kernel<24><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2, status);
+    else split_svd_kernel<32><<<S, 64, 0, st>>>(S11, S12, S22, K, s_train, s_test, u_repro, v_repro, s2, status);
     PLSB_LAUNCH_CHECK("split_svd_kernel");
     return PLSB200_OK;
 }

@@ -7,7 +7,7 @@ factorisation: every method's M is `Coef^T W` for a fixed coefficient matrix `Co
 already on the device (X itself, or its block z-scored copy Z for the behaviour methods), so
 
     M M^T = Coef^T (W W^T) Coef            K x K, from the Gram matrix the permutation test needs anyway
-    [U, s^2] = eig(M M^T)                  one warp of the Jacobi kernel (K <= 32; host LAPACK on the K x K above)
+    [U, s^2] = eig(M M^T)                  the Jacobi kernel (one warp up to K = 32, one CTA up to K = 112)
     V = W^T (Coef U diag(1/s))             one pass over W (salience kernel)
     X_latent = X V                         one pass over X (xv kernel)
 
@@ -30,13 +30,9 @@ NULL_RTOL = 1e-7
 
 def _eigh_desc(eng, B):
     """Eigen-decomposition of a small symmetric PSD device matrix: eigenvalues descending, vectors in columns (host)."""
-    K = int(B.shape[0])
-    if K <= 32:
-        ev, U = eng.sym_eig(B[None])
-        ev, U = eng.to_host(ev, U)
-        return ev[0], U[0]
-    w, U = np.linalg.eigh(B.cpu().numpy())
-    return w[::-1].copy(), U[:, ::-1].copy()
+    ev, U = eng.sym_eig(B[None])          # warp-level Jacobi up to K = 32, CTA-level up to 112 (csrc/split.cu)
+    ev, U = eng.to_host(ev, U)
+    return ev[0], U[0]
 
 
 def _fix_signs(U):

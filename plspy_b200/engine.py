@@ -466,13 +466,25 @@ class Engine:
 
     # ------------------------------------------------------------------ split-half (K3)
     def sym_eig(self, A):
-        """Batched symmetric eigendecomposition (B x K x K, K <= 32): evals descending, evecs in columns."""
+        """Batched symmetric eigendecomposition (B x K x K, K <= 112): evals descending, evecs in columns.
+        Raises if a matrix did not converge within the solver's sweep limit."""
         A = self.to_device(A, F64)
         B, K = int(A.shape[0]), int(A.shape[1])
         ev = self._empty(B, K); U = self._empty(B, K, K)
+        status = torch.empty(B, dtype=I32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib.plsb200_sym_eig_f64(self._p(A), K, B, self._p(ev), self._p(U), self._stream()), "sym_eig_f64")
+            check(lib.plsb200_sym_eig_f64(self._p(A), K, B, self._p(ev), self._p(U), self._p(status), self._stream()),
+                  "sym_eig_f64")
+        self._check_converged(status, "sym_eig")
         return ev, U
+
+    def _check_converged(self, status, what):
+        """One scalar read-back (the callers read the results back right after anyway): the Jacobi solvers flag
+        matrices that hit their sweep limit and such results must not be consumed."""
+        bad = int(status.sum().item())
+        if bad:
+            raise _lib.PlsB200Error(f"{what}: the Jacobi eigensolver did not converge for {bad} of {status.numel()} "
+                                    "matrices")
 
     def split_gram(self, idx1, idx2, A1, A2):
         """S11, S12, S22 (S x K x K) of the half-sample cross-block matrices M_h = A_h X[idx_h]."""
@@ -493,9 +505,13 @@ class Engine:
         S, K = int(S11.shape[0]), int(S11.shape[1])
         s1 = self._empty(S, K); s2 = self._empty(S, K)
         st = self._empty(S, K, K); ur = self._empty(S, K, K); vr = self._empty(S, K, K)
+        status = torch.empty(S, dtype=I32, device=self.device)
         with torch.cuda.device(self.device):
+            ws = self._ws(lib.plsb200_split_svd_f64_workspace(K, S))
             check(lib.plsb200_split_svd_f64(self._p(S11), self._p(S12), self._p(S22), K, S, self._p(s1), self._p(st),
-                                            self._p(ur), self._p(vr), self._p(s2), self._stream()), "split_svd_f64")
+                                            self._p(ur), self._p(vr), self._p(s2), self._p(status), self._p(ws),
+                                            ws.numel(), self._stream()), "split_svd_f64")
+        self._check_converged(status, "split_svd")
         return s1, st, ur, vr, s2
 
     # ------------------------------------------------------------------ behaviour PLS (K5)

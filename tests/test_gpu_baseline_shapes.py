@@ -47,7 +47,9 @@ def _compare_task(res, o, tol=1e-8):
     np.testing.assert_array_equal(rt.stepdown_ratio, o["perm"]["stepdown_ratio"])
     np.testing.assert_allclose(rt.perm_debug_dict["s_list"][:, live], o["perm"]["s_hat"][:, live], rtol=1e-10)
     np.testing.assert_allclose(rt.std_errs[:, live], o["boot"]["std_errs"][:, live], rtol=tol)
-    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=tol)
+    # (voxels whose original salience is ~0 carry V entries at LAPACK's rounding level, which differ between the two
+    # sides' own SVDs of the original data: absolute floor 1e-9 on ratios that are O(1..10) where they matter)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=tol, atol=1e-9)
     for i in (0, 1):
         np.testing.assert_allclose(rt.conf_ints[i][:, live], o["boot"]["conf_ints"][i][:, live], rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(rt.boot_debug_dict["Tdistrib"][:, :, live], o["boot"]["Tdistrib"][:, :, live],
@@ -84,7 +86,8 @@ def test_cfg3m_mct_200k_matches_oracle():
     np.random.seed(1237)
     fast = plspy_b200.PLS(X, groups, C, num_perm=16, num_boot=16, mctype=0, pls_method="mct", precision="tf32x3")
     np.testing.assert_array_equal(fast.resample_tests.permute_ratio, o["perm"]["permute_ratio"])
-    np.testing.assert_allclose(fast.resample_tests.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-4)
+    np.testing.assert_allclose(fast.resample_tests.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-4,
+                               atol=1e-9)
 
 
 def test_cfg5_rows_mct_n1200_matches_oracle():
@@ -99,7 +102,8 @@ def test_cfg5_rows_mct_n1200_matches_oracle():
     live = _compare_task(res, o)
     np.random.seed(1239)
     fast = plspy_b200.PLS(X, groups, C, num_perm=3, num_boot=4, mctype=0, pls_method="mct", precision="tf32x3")
-    np.testing.assert_allclose(fast.resample_tests.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-4)
+    np.testing.assert_allclose(fast.resample_tests.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-4,
+                               atol=1e-9)
 
 
 def test_cfg4_mb_bscan_200k_with_splits_matches_oracle():
@@ -120,7 +124,7 @@ def test_cfg4_mb_bscan_200k_with_splits_matches_oracle():
     np.testing.assert_array_equal(rt.stepdown_ratio, o["perm"]["stepdown_ratio"])
     np.testing.assert_allclose(rt.perm_debug_dict["s_list"][:, live], o["perm"]["s_hat"][:, live], rtol=1e-9)
     np.testing.assert_allclose(rt.std_errs[:, live], o["boot"]["std_errs"][:, live], rtol=1e-6)
-    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-6)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], o["boot"]["boot_ratios"][:, live], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(rt.LVcorr[:, :, live], o["boot"]["LVcorr"][:, :, live], rtol=1e-7, atol=1e-9)
     for i in (0, 1):
         np.testing.assert_allclose(rt.conf_ints[i][:, live], o["boot"]["conf_ints"][i][:, live], rtol=1e-7, atol=1e-9)

@@ -84,6 +84,13 @@ def test_wide_behaviour_design_k48():
     _check(o, res)
 
 
+def test_wide_behaviour_design_k48_split_half():
+    """the same 48-LV design with num_split > 0: the split-half SVDs go through the CTA-level Jacobi solver
+    (np.linalg.svd in the reference has no size limit: class_functions.py:122, split_half_resampling.py:194, 612)."""
+    o, res = _both("rb", (9, 8, 9), 4, 400, nb=4, nperm=3, nboot=3, nsplit=4, lv=2, seed=3)
+    _check(o, res, nsplit=4)
+
+
 def test_tiny_voxel_counts():
     for p in (1, 7, 65):
         o, res = _both("mct", (6, 6), 2, p, nperm=5, nboot=5, seed=10 + p)

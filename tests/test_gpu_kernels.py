@@ -195,10 +195,11 @@ def test_error_reporting(torch_cuda):
         eng.boot_moments(np.zeros((1400, 3)), np.zeros((2, 1400), np.int32))   # N > 1280 is not supported
 
 
-@pytest.mark.parametrize("K", [3, 6, 12, 16, 24, 32])
+@pytest.mark.parametrize("K", [3, 6, 12, 16, 24, 32, 33, 48, 64, 100, 112])
 def test_sym_eig_jacobi(torch_cuda, K):
-    """K3: warp-per-matrix one-sided Jacobi vs LAPACK (np.linalg.eigh) on PSD Gram matrices,
-    including rank-deficient ones.  North-star tolerance: singular values 1e-10 relative."""
+    """K3: one-sided Jacobi (warp per matrix up to K = 32, CTA per matrix with shared-memory columns up to 112) vs
+    LAPACK (np.linalg.eigh) on PSD Gram matrices, including rank-deficient ones.  North-star tolerance: singular
+    values 1e-10 relative."""
     from plspy_b200.engine import Engine
     rs = np.random.RandomState(K)
     B = 37
@@ -220,10 +221,19 @@ def test_sym_eig_jacobi(torch_cuda, K):
         np.testing.assert_allclose(np.sqrt(ev[b][:K // 2]), np.sqrt(s_ref[:K // 2]), rtol=1e-10)
 
 
-def test_split_gram_and_svd(torch_cuda):
+def test_sym_eig_rejects_k_beyond_shared_memory(torch_cuda):
+    from plspy_b200.engine import Engine
+    from plspy_b200._lib import PlsB200Error
+    eng = Engine(np.zeros((2, 2)))
+    with pytest.raises(PlsB200Error):
+        eng.sym_eig(np.eye(113)[None])
+
+
+@pytest.mark.parametrize("N,p,K,S,n1,n2", [(40, 500, 6, 9, 18, 22), (120, 900, 48, 5, 56, 64)])
+def test_split_gram_and_svd(torch_cuda, N, p, K, S, n1, n2):
+    """K = 48 takes the CTA-level eigensolver + split_out_kernel path of plsb200_split_svd_f64."""
     from plspy_b200.engine import Engine
     rs = np.random.RandomState(21)
-    N, p, K, S, n1, n2 = 40, 500, 6, 9, 18, 22
     X = rs.standard_normal((N, p))
     A1 = rs.standard_normal((K, n1)); A2 = rs.standard_normal((K, n2))
     i1 = np.array([rs.permutation(N)[:n1] for _ in range(S)], dtype=np.int32)
