@@ -21,6 +21,15 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+// The probe modes that isolate the limiter of the tcgen05 kernel (free-running roles, no producer, no epilogue
+// arithmetic: WRONG RESULTS by construction) exist only in builds with -DPLSB_PROBES (tools/); in the product library
+// TF_DBG is the constant 0 and every probe branch is compiled out.
+#ifdef PLSB_PROBES
+#define TF_DBG(a) ((a).dbg)
+#else
+#define TF_DBG(a) 0
+#endif
+
 namespace plsb {
 
 constexpr int TF_KB = 16;                 // rows per pipeline stage
@@ -52,13 +61,15 @@ static bool tf_plan(int N, int K, int R, int64_t p, TfPlan& t) {
     t.nks_last = (int)cdiv(N - TF_KB * (t.nkb - 1), 8);
     t.nct = (int)cdiv(R, t.nres);
     t.b_plane = (uint32_t)t.ntile * TF_KB * 4;
-    const char* env = getenv("PLSB200_TF32_CTA_GROUP");
+    static const char* const env = getenv("PLSB200_TF32_CTA_GROUP");      // read once per process
     // default: CTA pairs (23.4 ms on the bench workload vs 24.2 ms single-CTA once the epilogue stopped being the
     // limiter: the pair moves a third less data through L2 and shared memory); PLSB200_TF32_CTA_GROUP=1 selects the
     // single-CTA kernel
     t.cg = (env && env[0] == '1') ? 1 : 2;
+#ifdef PLSB_PROBES
     const char* dbg = getenv("PLSB200_TF32_DEBUG");     // the no-producer probe modes only make sense without the relay
     if (dbg && (dbg[0] == '2' || dbg[0] == '4')) t.cg = 1;
+#endif
     t.stage_bytes = TF_A_STAGE + 2 * t.b_plane / t.cg;
     int ns = (int)((227 * 1024 - 2048) / t.stage_bytes);
     if (ns > 8) ns = 8;
@@ -223,7 +234,7 @@ struct TfArgs {
     int K, R, nkb, nks_last, ntile, nres, nct, ct_per_split, nstage;
     uint32_t b_plane, stage_bytes;
     long long* trace;      // optional (PLSB200_TF32_TRACE=1): per-CTA cycle counters of the role loops, 8 per CTA
-    int dbg;               // development only (PLSB200_TF32_DEBUG): 1 = producer and MMA issuer free-running (no full /
+    int dbg;               // probe builds only (-DPLSB_PROBES, tools/): PLSB200_TF32_DEBUG 1 = producer and MMA issuer free-running (no full /
                            // empty hand-shake: wrong results, isolates contention from waiting), 2 = no producer at all
 };
 
@@ -354,8 +365,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 for (int ct = ct0; ct < ct1; ++ct) {
                     const char* bsrc = reinterpret_cast<const char*>(a.bimg) + (size_t)ct * a.nkb * (2u * a.b_plane);
                     for (int kb = 0; kb < a.nkb; ++kb) {
-                        if (a.dbg == 2 || a.dbg == 4) continue;
-                        if (a.dbg == 0 || a.dbg == 3 || a.dbg == 5) mbar_wait(empty + stage, phase ^ 1u);
+                        if (TF_DBG(a) == 2 || TF_DBG(a) == 4) continue;
+                        if (TF_DBG(a) == 0 || TF_DBG(a) == 3 || TF_DBG(a) == 5) mbar_wait(empty + stage, phase ^ 1u);
                         unsigned char* dst = ring + (size_t)stage * a.stage_bytes;
                         mbar_expect_tx(full + stage, cta_stage_bytes);
                         bulk_g2s(dst, asrc + (size_t)kb * TF_A_STAGE, TF_A_STAGE, full + stage);
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                     const uint32_t d = tbase + (uint32_t)as * 256u;
                     uint32_t accum = 0u;
                     for (int kb = 0; kb <= last_kb; ++kb) {
-                        if (a.dbg == 0 || a.dbg == 3 || a.dbg == 5) {
+                        if (TF_DBG(a) == 0 || TF_DBG(a) == 3 || TF_DBG(a) == 5) {
                             mbar_wait(full + stage, phase);
                             if constexpr (CG == 2) mbar_wait_cluster(pfull + stage, phase);
                         }
@@ -452,7 +463,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                 tc_fence_after();
                 const uint32_t t0 = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * 256u;
                 const int nvalid = min(a.nres, a.R - ct * a.nres) * KP;     // valid columns of this tile
-                if (a.dbg == 5) {
+                if (TF_DBG(a) == 5) {
                     // development only: all the tensor-memory loads of a tile, none of the arithmetic
                     for (int c0 = 0; c0 < a.ntile; c0 += 16) {
                         uint32_t x[16];
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) boot_moments_tf32_kernel(const 
                         tmem_ld_wait();
                         s1[0] += (double)__uint_as_float(x[c0 & 15]);
                     }
-                } else if (a.dbg >= 3) {
+                } else if (TF_DBG(a) >= 3) {
                     // development only: drain the accumulator without the FP64 fold
                     uint32_t x[16];
                     tmem_ld16(t0, x);
@@ -651,7 +662,10 @@ extern "C" int plsb200_boot_moments_tf32(const void* ximage, int N, int64_t p, c
     a.K = K; a.R = R; a.nkb = t.nkb; a.nks_last = t.nks_last; a.ntile = t.ntile; a.nres = t.nres; a.nct = t.nct;
     a.ct_per_split = t.ct_per_split; a.nstage = t.nstage; a.b_plane = t.b_plane; a.stage_bytes = t.stage_bytes;
     a.trace = nullptr;
+    a.dbg = 0;
+#ifdef PLSB_PROBES
     a.dbg = getenv("PLSB200_TF32_DEBUG") ? atoi(getenv("PLSB200_TF32_DEBUG")) : 0;
+#endif
     int rc;
     switch (t.Kp) {
 #define PLSB_TF(kp) case kp: rc = launch_tf32<kp>(t, a, st); break;

@@ -215,8 +215,8 @@ extern "C" int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin,
                                          void* stream) {
     PLSB_CHECK_ARG(Xstd && Xlin && ids && Q && segs && S3 && workspace, "half_gram_win_f64: null pointer");
     PLSB_CHECK_ARG(p > 0 && nseg > 0 && nq > 0 && (nq & 1) == 0 && nmax > 0 && K > 0 && ns > 0, "half_gram_win_f64: bad shape");
-    if (K > 32) {
-        set_err("half_gram_win_f64: K=%d > 32 not supported", K);
+    if (K > 96) {      // the 2 x K rows of a 128-voxel tile must fit in shared memory (203 KB at K = 96)
+        set_err("half_gram_win_f64: K=%d > 96 not supported", K);
         return PLSB200_EUNSUPPORTED;
     }
     const int ntile = (int)cdiv(p, HG_VT);
@@ -230,7 +230,7 @@ extern "C" int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin,
     do {                                                                                                          \
         size_t smem = ((size_t)2 * KCV * (HG_VT + 4) + (size_t)nq + (size_t)nmax) * sizeof(double) +        \
                       (size_t)2 * nseg * HG_SEG * sizeof(int);                                                    \
-        if (smem > 220 * 1024) { set_err("half_gram_win_f64: halves too large for shared memory"); return PLSB200_EUNSUPPORTED; } \
+        if (smem > 227 * 1024) { set_err("half_gram_win_f64: halves too large for shared memory"); return PLSB200_EUNSUPPORTED; } \
         PLSB_CUDA(cudaFuncSetAttribute(half_gram_win_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         half_gram_win_kernel<KCV><<<ntile, HG_VT, smem, st>>>(Xstd, Xlin, p, ids, Q, segs, nseg, nq, nmax, K, s0, \
                                                               ns, (double*)workspace);                            \
@@ -238,7 +238,10 @@ extern "C" int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin,
     if (K <= 8) PLSB_HGW_LAUNCH(8);
     else if (K <= 16) PLSB_HGW_LAUNCH(16);
     else if (K <= 24) PLSB_HGW_LAUNCH(24);
-    else PLSB_HGW_LAUNCH(32);
+    else if (K <= 32) PLSB_HGW_LAUNCH(32);
+    else if (K <= 48) PLSB_HGW_LAUNCH(48);
+    else if (K <= 64) PLSB_HGW_LAUNCH(64);
+    else PLSB_HGW_LAUNCH(96);
 #undef PLSB_HGW_LAUNCH
     PLSB_LAUNCH_CHECK("half_gram_win_kernel");
     const long long n = (long long)ns * 3 * K * K;

@@ -34,6 +34,18 @@ __device__ __forceinline__ int jacobi_warp(double (&w)[KM], double (&v)[KM], dou
     constexpr int n = KM;          // even
     const double tol = 4.0 * DBL_EPSILON;
     converged = false;
+    // Columns whose norm has fallen to the rounding level of the matrix (||w_j|| = lambda_j <= n eps lambda_max: the
+    // null space of a rank-deficient Gram block, e.g. mctype 3 or repeated rows) are pure noise: their cosines with the
+    // other columns never drop below `tol`, so they are left alone instead of being rotated for ever.
+    double nul;
+    {
+        double own = 0.0;
+#pragma unroll
+        for (int e = 0; e < KM; ++e) own = fma(w[e], w[e], own);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) own = fmax(own, __shfl_xor_sync(0xffffffffu, own, o));
+        nul = own * ((double)n * DBL_EPSILON) * ((double)n * DBL_EPSILON);
+    }
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
         bool rotated = false;
 #pragma unroll 1
@@ -58,7 +70,7 @@ __device__ __forceinline__ int jacobi_warp(double (&w)[KM], double (&v)[KM], dou
             }
             const bool lo = lane < partner;
             const double alpha = lo ? own : oth, beta = lo ? oth : own;   // (i < j) orientation
-            const bool rot = active && gam != 0.0 && fabs(gam) > tol * sqrt(alpha * beta);
+            const bool rot = active && gam != 0.0 && alpha > nul && beta > nul && fabs(gam) > tol * sqrt(alpha * beta);
             double co = 1.0, so = 0.0;
             if (rot) {
                 rotated = true;
@@ -154,6 +166,18 @@ __global__ void __launch_bounds__(1024) sym_eig_cta_kernel(const double* __restr
             V[i] = (c == e) ? 1.0 : 0.0;
         }
         __syncthreads();
+        // rounding-level columns are left alone (see jacobi_warp)
+        for (int c = warp; c < n; c += nw) {
+            double nn = 0.0;
+            for (int e = lane; e < n; e += 32) nn = fma(W[(size_t)c * n + e], W[(size_t)c * n + e], nn);
+            nn = warp_sum(nn);
+            if (lane == 0) lam[c] = nn;
+        }
+        __syncthreads();
+        double nul = 0.0;
+        for (int c = 0; c < n; ++c) nul = fmax(nul, lam[c]);
+        nul *= ((double)n * DBL_EPSILON) * ((double)n * DBL_EPSILON);
+        __syncthreads();
         bool conv = false;
         for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS && !conv; ++sweep) {
             if (tid == 0) any_rot = 0;
@@ -174,7 +198,7 @@ __global__ void __launch_bounds__(1024) sym_eig_cta_kernel(const double* __restr
                         alpha = fma(a, a, alpha); beta = fma(c, c, beta); gam = fma(a, c, gam);
                     }
                     alpha = warp_sum(alpha); beta = warp_sum(beta); gam = warp_sum(gam);
-                    if (gam != 0.0 && fabs(gam) > tol * sqrt(alpha * beta)) {
+                    if (gam != 0.0 && alpha > nul && beta > nul && fabs(gam) > tol * sqrt(alpha * beta)) {
                         const double zeta = (beta - alpha) / (2.0 * gam);
                         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                         const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;

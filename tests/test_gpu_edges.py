@@ -87,7 +87,9 @@ def test_wide_behaviour_design_k48():
 def test_wide_behaviour_design_k48_split_half():
     """the same 48-LV design with num_split > 0: the split-half SVDs go through the CTA-level Jacobi solver
     (np.linalg.svd in the reference has no size limit: class_functions.py:122, split_half_resampling.py:194, 612)."""
-    o, res = _both("rb", (9, 8, 9), 4, 400, nb=4, nperm=3, nboot=3, nsplit=4, lv=2, seed=3)
+    # (groups of 11-12 subjects: every half block keeps >= 5 subjects, so the 4 behaviours of a block stay full rank
+    # and all 48 latent variables of the halves are live)
+    o, res = _both("rb", (12, 11, 12), 4, 400, nb=4, nperm=3, nboot=3, nsplit=4, lv=2, seed=3)
     _check(o, res, nsplit=4)
 
 
