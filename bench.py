@@ -449,9 +449,13 @@ def run_gpu(args):
     U, s, V = cf._run_pls(X_mc)
     Tvsc = cf._get_group_condition_means(X @ V, co)
     # index matrices: this rank's shard of the global range, reference RNG call order
+    # (weak scaling: every rank draws ITS OWN shard from its own stream -- deliberately rank-dependent, hence outside
+    # the collective run whose index draws insist on identical streams, dist.assert_identical_rng)
+    from plspy_b200 import dist as pdist
     np.random.seed(1234 + 3 + rank)
-    idx_p = resample.permutation_indices("mct", nperm, co)[0]
-    idx_b = resample.bootstrap_indices("mct", nboot, co)[0]
+    with pdist.local_only():
+        idx_p = resample.permutation_indices("mct", nperm, co)[0]
+        idx_b = resample.bootstrap_indices("mct", nboot, co)[0]
     gp = np.zeros((nperm * world, N), np.int32); gp[rank * nperm:(rank + 1) * nperm] = idx_p
     gb = np.zeros((nboot * world, N), np.int32); gb[rank * nboot:(rank + 1) * nboot] = idx_b
 
@@ -466,8 +470,9 @@ def run_gpu(args):
         # strong scaling: the SAME fixed job as the N = 1 run (nperm + nboot in total, identical index matrices on
         # every rank), sharded over the ranks
         np.random.seed(1234 + 3)
-        sp = torch.from_numpy(resample.permutation_indices("mct", nperm, co)[0].astype(np.int32)).pin_memory()
-        sb = torch.from_numpy(resample.bootstrap_indices("mct", nboot, co)[0].astype(np.int32)).pin_memory()
+        with pdist.local_only():
+            sp = torch.from_numpy(resample.permutation_indices("mct", nperm, co)[0].astype(np.int32)).pin_memory()
+            sb = torch.from_numpy(resample.bootstrap_indices("mct", nboot, co)[0].astype(np.int32)).pin_memory()
         jobs["strong"] = (nperm, nboot, sp, sb, sp.to(dev), sb.to(dev))
     torch.cuda.synchronize()
 
@@ -558,7 +563,6 @@ def run_gpu(args):
     # ---- strong scaling (N > 1): the fixed N = 1 job sharded over the ranks, next to the same job on rank 0 alone
     strong = None
     if world > 1 and not args.no_strong:
-        from plspy_b200 import dist as pdist
         modes = [args.precision] + (["tf32x3"] if fast is not None else [])
         sm = {m: measure(m, "strong") for m in modes}
         tp, tb, sph, sbh, spd, sbd = jobs["strong"]

@@ -10,7 +10,7 @@ boot_ratios, [LVcorr], boot_debug_dict, CI`; "NA" placeholders when a test is sk
 
 Extra keyword-only arguments (not in the reference): `perm_indices`, `boot_indices` (index matrices
 generated elsewhere -- each an int array, or a (task, behaviour) tuple for mb/cmb), `engine`
-(an `Engine` that already holds X on the device), `precision` ("fp64" exact mode, or "tf32x3": the
+(an `Engine` that already holds X on the device), `device` (CUDA device of the engine built here), `precision` ("fp64" exact mode, or "tf32x3": the
 bootstrap moment GEMM of the task methods on the tcgen05 tensor cores; p-values stay FP64-exact).
 """
 import abc
@@ -89,6 +89,31 @@ class _LazyDebugDict(dict):
 
     def keys(self):
         return list(dict.keys(self)) + list(self._lazy.keys())
+
+    # every other read access sees the lazy entries too (the reference returns a plain dict with every key present)
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._lazy)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def materialize(self):
+        """Compute every pending entry (may be large: `right_sv_sampled` is B x p x K)."""
+        for key in list(self._lazy):
+            self[key]
+        return self
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def copy(self):
+        return dict(self.items())
 
 
 def _stepdown_tail(s):
@@ -314,7 +339,8 @@ class _ResampleTestPLS(ResampleTest):
 
     def __init__(self, X, Y, U, s, V, cond_order, mctype, contrast=None, preprocess=None, nperm=1000,
                  nboot=1000, bscan=None, Xbscan=None, Ybscan=None, lvcorrs_orig=None, Tvsc_orig=None,
-                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None, precision="fp64", rotate_method=2):
+                 CI=0.95, *, perm_indices=None, boot_indices=None, engine=None, precision="fp64", rotate_method=2,
+                 device=None):
         self.CI = CI
         if rotate_method not in (0, 1, 2):
             raise ValueError("rotate_method must be 0 (SVD), 1 (Procrustes) or 2 (derived)")
@@ -323,7 +349,7 @@ class _ResampleTestPLS(ResampleTest):
         self.rotate_method = rotate_method
         _log(f"PLS ALG: {self.pls_alg}")
         eng = engine if engine is not None else (
-            Engine(X, precision=precision) if (nperm > 0 or nboot > 0) else None)
+            Engine(X, device=device, precision=precision) if (nperm > 0 or nboot > 0) else None)
         self._engine = eng
         if eng is not None and self.pls_alg in ("mct", "cst") and dist.world()[1] > 1:
             eng.gram_collective()          # all ranks are here: Gram from per-rank voxel ranges + one all-reduce

@@ -1,17 +1,23 @@
 // K4 for tall designs (N > 320 rows): row-split variant of boot_moments_kernel.
 //
 // The A fragments of 8 voxels x N rows no longer fit one warp's registers, so RS (2 or 4) warps share a
-// voxel group and each keeps N/RS rows resident.  A pipeline stage is ONE 8-column block of the packed
-// coefficients for all rows (RS*NKS k-steps, <= 82 KB), every warp runs its NKS-long DMMA chain on its own
-// row range, the partial D fragments are exchanged through shared memory (double-buffered, one named
-// barrier per block) and the warp with row-chunk 0 folds (VS - pivot) into the running moments.
-// The accumulator set rotates with the block index modulo NACC = period / 8 columns.
+// voxel group and each keeps N/RS rows resident (NKS k-steps of 4 rows).  As in boot_moments_kernel a warp works
+// on a whole PERIOD of 8*NACC columns at a time, i.e. NACC independent accumulator chains that are kept
+// round-robin so that the DMMA pipe always has NACC MMAs in flight per warp (a single chain per warp -- the first
+// version of this kernel, one 8-column block per stage -- ran at 0.63 of the DGEMM peak, bound by the DMMA latency).
+// A period's coefficients for all rows (RS*NKS*NACC*256 B: 230 KB at N = 1200, K = 24) exceed shared memory, so
+// a period is streamed as NSUB = 4 pipeline stages of CK = NKS/4 k-steps per row chunk; the accumulators live
+// across the four stages.  Once per period the RS partial D fragments of a voxel group are exchanged through shared
+// memory (double-buffered, one named barrier per period and voxel group) and the warp with row-chunk 0 folds
+// (VS - pivot) into the running moments.
 #include "common.cuh"
 
 namespace plsb {
 
+constexpr int RS_NSUB = 4;       // pipeline stages per period
+
 struct RsPlan {
-    int Kp, nacc, nb, rs, nks, stot, ncb, nstage, nsplit, cb_per_split, vox;
+    int Kp, nacc, nb, rs, nks, ck, nper, nstage, nsplit, per_per_split, vox;
     size_t stage_doubles, smem_bytes;
 };
 
@@ -30,41 +36,42 @@ static bool rs_plan(int N, int K, int R, int64_t p, RsPlan& b) {
     int nks = (int)cdiv(cdiv(ksteps, b.rs), 8) * 8;      // buckets of 8 k-steps: 48, 56, 64, 72, 80
     if (nks < 48) nks = 48;
     if (nks > 80) return false;                          // N > 1280
-    b.nks = nks; b.stot = nks * b.rs;
-    b.ncb = (int)cdiv(R, b.nb) * b.nacc;
-    b.stage_doubles = (size_t)b.stot * 32;
+    b.nks = nks; b.ck = nks / RS_NSUB;
+    b.nper = (int)cdiv(R, b.nb);
+    b.stage_doubles = (size_t)b.rs * b.ck * b.nacc * 32;
     b.vox = 8 * (8 / b.rs);
-    const size_t extra = (size_t)(8 / b.rs) * 16 * b.Kp * 8 + (size_t)2 * (8 / b.rs) * (b.rs - 1) * 64 * 8 + 256;
+    const size_t extra = (size_t)(8 / b.rs) * 16 * b.Kp * 8 +
+                         (size_t)2 * (8 / b.rs) * (b.rs - 1) * 64 * b.nacc * 8 + 256;
     int ns = (int)((227 * 1024 - extra) / (b.stage_doubles * 8));
-    if (ns > 4) ns = 4;
+    if (ns > 6) ns = 6;
     if (ns < 2) return false;
     b.nstage = ns;
     b.smem_bytes = ns * b.stage_doubles * 8 + extra;
     const int64_t tiles = cdiv(p > 0 ? p : 1, b.vox);
     const int nsm = num_sms();
-    const int nper = b.ncb / b.nacc;
     int best = 1; double best_cost = 1e30;
     for (int n = 1; n <= 8; ++n) {
-        if (n > 1 && nper / n < 8) break;
+        if (n > 1 && b.nper / n < 8) break;
         const double waves = (double)tiles * n / nsm;
         const double cost = ceil(waves) / waves + 0.004 * (n - 1);
         if (cost < best_cost - 1e-12) { best_cost = cost; best = n; }
     }
-    const int per_per_split = (int)cdiv(nper, best);
-    b.cb_per_split = per_per_split * b.nacc;
-    b.nsplit = (int)cdiv(nper, per_per_split);
+    b.per_per_split = (int)cdiv(b.nper, best);
+    b.nsplit = (int)cdiv(b.nper, b.per_per_split);
     return true;
 }
 
-// packed layout: offset(cb, s, lane) = (cb*stot + s)*32 + lane ; column j = r*Kp + k -> cb = j/8, n = j%8 ;
-// row i -> chunk rc = i / (4*nks), s = rc*nks + (i % (4*nks))/4, q = i%4 ; lane = 4n + q
+// packed layout: offset(per, sub, rc, s_in, jb, lane) = ((((per*NSUB + sub)*rs + rc)*ck + s_in)*nacc + jb)*32 + lane
+// column-in-period c = (r % nb)*Kp + k -> jb = c/8, n = c%8 ; row i -> chunk rc = i / (4*nks), k-step of the chunk
+// s = (i % (4*nks))/4 -> sub = s / ck, s_in = s % ck ; q = i%4 ; lane = 4n + q
 __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restrict__ E, int N, int K,
-                                                          const int32_t* __restrict__ idx, int Kp, int stot,
-                                                          double* __restrict__ coef) {
+                                                          const int32_t* __restrict__ idx, int Kp, int nacc, int nb,
+                                                          int rs, int nks, int ck, double* __restrict__ coef) {
     extern __shared__ int ids[];          // E (N x K) stays in global memory: L1/L2-resident, read via __ldg
     const int r = blockIdx.x;
     for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
     __syncthreads();
+    const int per = r / nb, cbase = (r % nb) * Kp;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         double acc[24];
 #pragma unroll
@@ -75,12 +82,14 @@ __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restr
                 for (int k = 0; k < 24; ++k)
                     if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
             }
-        const int s = i >> 2, q = i & 3;
+        const int rc = i / (4 * nks), s = (i % (4 * nks)) >> 2, q = i & 3;
+        const int sub = s / ck, s_in = s % ck;
+        const size_t base = ((((size_t)per * RS_NSUB + sub) * rs + rc) * ck + s_in) * nacc;
 #pragma unroll
         for (int k = 0; k < 24; ++k)
             if (k < K) {
-                const long long j = (long long)r * Kp + k;
-                coef[((size_t)(j >> 3) * stot + s) * 32 + 4 * (int)(j & 7) + q] = acc[k];
+                const int c = cbase + k;
+                coef[(base + (c >> 3)) * 32 + 4 * (c & 7) + q] = acc[k];
             }
     }
 }
@@ -88,26 +97,26 @@ __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restr
 template <int NKS, int NACC, int RS>
 __global__ void __launch_bounds__(256, 1)
 boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
-                       const double* __restrict__ coef, int ncb, int cb_per_split, int nstage, int R, int Kp, int K,
+                       const double* __restrict__ coef, int nper, int per_per_split, int nstage, int R, int Kp, int K,
                        const double* __restrict__ pivot, double* __restrict__ osum, double* __restrict__ osumsq) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int NVG = 8 / RS;                    // voxel groups per CTA
-    constexpr int STOT = NKS * RS;
-    constexpr int stage_doubles = STOT * 32;
+    constexpr int CK = NKS / RS_NSUB;              // k-steps per row chunk and stage
+    constexpr int stage_doubles = RS * CK * NACC * 32;
     constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
     double* ring = reinterpret_cast<double*>(smraw);
     double* red = ring + (size_t)nstage * stage_doubles;                 // [NVG][2][8][Kp]
-    double* exch = red + NVG * 16 * Kp;                                  // [2][NVG][RS-1][32][2]
-    uint64_t* full = reinterpret_cast<uint64_t*>(exch + 2 * NVG * (RS - 1) * 64);
+    double* exch = red + NVG * 16 * Kp;                                  // [2][NVG][RS-1][NACC][32][2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(exch + 2 * NVG * (RS - 1) * 64 * NACC);
     uint64_t* empty = full + nstage;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int vg = warp / RS, rc = warp % RS;
     const int q = lane & 3, vr = lane >> 2;
     const long long v = (long long)blockIdx.x * (NVG * 8) + vg * 8 + vr;
-    const int cb0 = blockIdx.y * cb_per_split;
-    const int cb1 = min(ncb, cb0 + cb_per_split);
-    const int nit = cb1 - cb0;
+    const int per0 = blockIdx.y * per_per_split;
+    const int per1 = min(nper, per0 + per_per_split);
+    const int nit = (per1 - per0) * RS_NSUB;       // pipeline stages of this CTA
 
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
@@ -116,7 +125,7 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
     __syncthreads();
     auto issue = [&](int it, int slot) {
         mbar_expect_tx(full + slot, stage_bytes);
-        const char* src = reinterpret_cast<const char*>(coef + (size_t)(cb0 + it) * stage_doubles);
+        const char* src = reinterpret_cast<const char*>(coef + ((size_t)per0 * RS_NSUB + it) * stage_doubles);
         char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
 #pragma unroll 1
         for (uint32_t off = 0; off < stage_bytes; off += 16384u)
@@ -124,6 +133,14 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
     };
     if (tid == 0)
         for (int it = 0; it < min(nstage, nit); ++it) issue(it, it);
+    // Refills are issued by whichever warp is the LAST to drain a slot (a shared-memory counter per slot tells it so):
+    // stage j + nstage goes out at the earliest possible moment and nobody waits for anybody.  (Thread 0 waiting on
+    // the `empty` barrier before each of its own stages -- the scheme of boot_moments_kernel -- kept warp 0 in lock-step
+    // with the slowest warp of the CTA at every stage, four times per period here; probing the barrier without
+    // blocking at stage boundaries delayed the refills by up to a stage and was slower still: 24.6 vs 28.0 TFLOP/s.)
+    int* drained = reinterpret_cast<int*>(empty + nstage);     // [nstage]
+    if (tid < nstage) drained[tid] = 0;
+    __syncthreads();
 
     double a[NKS];
 #pragma unroll
@@ -142,47 +159,74 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
         }
     const int nb = 8 * NACC / Kp;
 
-    int slot = 0, prev_slot = 0;
-    uint32_t phase = 0, prev_phase = 0;
-    for (int it0 = 0; it0 < nit; it0 += NACC) {
+    // the two warps of an SM sub-partition (w and w + 4) run about one stage apart, so that one of them has its MMA
+    // stream in flight while the other exchanges / folds its accumulators at a period boundary
+    if (warp >= 4) __nanosleep((unsigned)(CK * NACC * 8));
+
+    int slot = 0, it = 0;
+    uint32_t phase = 0;
+    for (int per = per0; per < per1; ++per) {
+        double d[NACC][2];
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            const int it = it0 + j;
-            if (it >= nit) break;
-            if (tid == 0 && it > 0) {
-                const int nx = it - 1 + nstage;
-                if (nx < nit) {
-                    mbar_wait(empty + prev_slot, prev_phase);
-                    issue(nx, prev_slot);
+        for (int j = 0; j < NACC; ++j) { d[j][0] = -piv[j][0]; d[j][1] = -piv[j][1]; }
+#pragma unroll
+        for (int sub = 0; sub < RS_NSUB; ++sub, ++it) {
+            mbar_wait(full + slot, phase);
+            // volatile: keeps the loads in program order (k-step major, chains round-robin), see boot_moments_kernel
+            const volatile double* bs = ring + (size_t)slot * stage_doubles + (size_t)rc * CK * NACC * 32 + lane;
+#pragma unroll
+            for (int s = 0; s < CK; ++s) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                    const double b = bs[(s * NACC + j) * 32];
+                    dmma884(d[j][0], d[j][1], a[sub * CK + s], b);
                 }
             }
             __syncwarp();
-            mbar_wait(full + slot, phase);
-            double d0 = -piv[j][0], d1 = -piv[j][1];
-            const volatile double* bs = ring + (size_t)slot * stage_doubles + (size_t)rc * NKS * 32 + lane;
-#pragma unroll
-            for (int s = 0; s < NKS; ++s) {
-                const double b = bs[s * 32];
-                dmma884(d0, d1, a[s], b);
+            if (lane == 0) {
+                mbar_arrive(empty + slot);
+                if (atomicAdd(drained + slot, 1) == 7) {        // this warp is the last of the eight: refill the slot
+                    drained[slot] = 0;
+                    if (it + nstage < nit) {
+                        mbar_wait(empty + slot, phase);          // (complete: orders the eight warps' reads before the copy)
+                        issue(it + nstage, slot);
+                    }
+                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);
-            // combine the RS partial fragments of this voxel group
-            double* ex = exch + (size_t)((it & 1) * NVG + vg) * (RS - 1) * 64;
-            if (rc > 0) {
-                ex[(rc - 1) * 64 + lane * 2] = d0;
-                ex[(rc - 1) * 64 + lane * 2 + 1] = d1;
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + vg), "r"(RS * 32) : "memory");
-            if (rc == 0) {
-#pragma unroll
-                for (int c = 0; c < RS - 1; ++c) { d0 += ex[c * 64 + lane * 2]; d1 += ex[c * 64 + lane * 2 + 1]; }
-                const long long col0 = (long long)(cb0 + it) * 8 + 2 * q;     // flattened (resample, k) column
-                if (col0 / Kp < R) { s1[j][0] += d0; s2[j][0] = fma(d0, d0, s2[j][0]); }
-                if ((col0 + 1) / Kp < R) { s1[j][1] += d1; s2[j][1] = fma(d1, d1, s2[j][1]); }
-            }
-            prev_slot = slot; prev_phase = phase;
             if (++slot == nstage) { slot = 0; phase ^= 1u; }
+        }
+        // combine the RS partial fragments of this voxel group, once per period
+        double* ex = exch + (size_t)(((per - per0) & 1) * NVG + vg) * (RS - 1) * 64 * NACC;
+        if (rc > 0) {
+#pragma unroll
+            for (int j = 0; j < NACC; ++j)
+                *reinterpret_cast<double2*>(ex + ((size_t)((rc - 1) * NACC + j) * 32 + lane) * 2) =
+                    make_double2(d[j][0], d[j][1]);
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + vg), "r"(RS * 32) : "memory");
+        if (rc == 0) {
+#pragma unroll
+            for (int c = 0; c < RS - 1; ++c)
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                    const double2 o = *reinterpret_cast<const double2*>(ex + ((size_t)(c * NACC + j) * 32 + lane) * 2);
+                    d[j][0] += o.x; d[j][1] += o.y;
+                }
+            const int rbase = per * nb;
+            if ((per + 1) * nb <= R) {                        // every slot of the period is a real resample
+#pragma unroll
+                for (int j = 0; j < NACC; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { s1[j][e] += d[j][e]; s2[j][e] = fma(d[j][e], d[j][e], s2[j][e]); }
+            } else {                                          // ragged last period: mask the padding slots
+#pragma unroll
+                for (int j = 0; j < NACC; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (rbase + (8 * j + 2 * q + e) / Kp < R) {
+                            s1[j][e] += d[j][e]; s2[j][e] = fma(d[j][e], d[j][e], s2[j][e]);
+                        }
+            }
         }
     }
     if (rc != 0) return;
@@ -230,7 +274,7 @@ static int rs_launch(const RsPlan& b, const double* X, int N, int64_t p, int64_t
     PLSB_CUDA(cudaFuncSetAttribute(boot_moments_rs_kernel<NKS, NACC, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)b.smem_bytes));
     dim3 grid((unsigned)cdiv(p, b.vox), (unsigned)b.nsplit);
-    boot_moments_rs_kernel<NKS, NACC, RS><<<grid, 256, b.smem_bytes, st>>>(X, ldx, N, p, coef, b.ncb, b.cb_per_split,
+    boot_moments_rs_kernel<NKS, NACC, RS><<<grid, 256, b.smem_bytes, st>>>(X, ldx, N, p, coef, b.nper, b.per_per_split,
                                                                           b.nstage, R, b.Kp, K, pivot, o1, o2);
     PLSB_LAUNCH_CHECK("boot_moments_rs_kernel");
     return PLSB200_OK;
@@ -262,7 +306,7 @@ static int rs_dispatch_nacc(const RsPlan& b, const double* X, int N, int64_t p, 
 size_t boot_rs_coef_bytes(int N, int K, int R) {
     RsPlan b;
     if (!rs_plan(N, K, R, 1, b)) return 0;
-    return (size_t)b.ncb * b.stage_doubles * sizeof(double);
+    return (size_t)b.nper * RS_NSUB * b.stage_doubles * sizeof(double);
 }
 
 size_t boot_rs_workspace(int N, int64_t p, int K, int R) {
@@ -277,9 +321,9 @@ int boot_rs_pack(const double* E, int N, int K, const int32_t* idx, int R, doubl
         set_err("boot_coef_pack_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=1280)", N, K, R);
         return PLSB200_EUNSUPPORTED;
     }
-    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.ncb * b.stage_doubles * sizeof(double), st));
+    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * RS_NSUB * b.stage_doubles * sizeof(double), st));
     size_t smem = (size_t)N * sizeof(int);
-    boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.stot, coef);
+    boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nacc, b.nb, b.rs, b.nks, b.ck, coef);
     PLSB_LAUNCH_CHECK("boot_rs_pack_kernel");
     return PLSB200_OK;
 }

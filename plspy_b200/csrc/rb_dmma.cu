@@ -238,25 +238,29 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
         const volatile double* bs = ring + (size_t)slot * coef_doubles + lane;
         const volatile double* ws = wring + ((bb + 1) % WSLOTS) * w_doubles + q;     // (stale but harmless when !has_next)
 
-        // ---- P_c = X_c^T Q_c of bootstrap bb on the tensor cores, folded into VS with the cell's scale; in the
-        //      shadow of the DMMAs, the weighted block moments of bootstrap bb+1 on the same resident fragments
-        double d[NBLK][2], vs[NBLK][2], m1 = 0.0, m2 = 0.0;
+        // ---- VS = sum_c sc_c(v) X_c^T Q_c of bootstrap bb on the tensor cores.  The (cell, voxel) scale multiplies
+        //      the A fragment (a lane's element x[s] belongs to voxel `vr` and to the cell of k-step s), so the NBLK
+        //      accumulator chains run through the whole bootstrap without being drained and restarted at every cell
+        //      boundary (the first version folded sc * D per cell: a 5-deep chain, then a full DMMA-latency stall).
+        //      In the shadow of the DMMAs: the weighted block moments of bootstrap bb+1 on the same resident fragments.
+        double vs[NBLK][2], m1 = 0.0, m2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NBLK; ++j) { d[j][0] = d[j][1] = 0.0; vs[j][0] = vs[j][1] = 0.0; }
+        for (int j = 0; j < NBLK; ++j) vs[j][0] = vs[j][1] = 0.0;
         {
             int cell = 0;
+            double sc = sct[vr];
 #pragma unroll
             for (int s = 0; s < NKS; ++s) {
+                const double xs = x[s] * sc;
 #pragma unroll
                 for (int j = 0; j < NBLK; ++j) {
                     const double b = bs[(s * NBLK + j) * 32];
-                    dmma884(d[j][0], d[j][1], x[s], b);
+                    dmma884(vs[j][0], vs[j][1], xs, b);
                 }
                 const double wx = ws[4 * s] * x[s];
                 m1 += wx;
                 m2 = fma(wx, x[s], m2);
                 if ((a.cend[s >> 5] >> (s & 31)) & 1u) {          // warp-uniform: last k-step of a cell
-                    const double sc = sct[cell * 8 + vr];
                     m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
                     m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
                     m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
@@ -264,12 +268,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                     if (q == 0) { mt[(cell * 8 + vr) * 2] = m1; mt[(cell * 8 + vr) * 2 + 1] = m2; }
                     ++cell;
                     m1 = m2 = 0.0;
-#pragma unroll
-                    for (int j = 0; j < NBLK; ++j) {
-                        vs[j][0] = fma(sc, d[j][0], vs[j][0]);
-                        vs[j][1] = fma(sc, d[j][1], vs[j][1]);
-                        d[j][0] = d[j][1] = 0.0;
-                    }
+                    sc = cell < a.ncell ? sct[cell * 8 + vr] : 0.0;   // (padding k-steps after the last cell: x = 0)
                 }
             }
         }

@@ -34,6 +34,30 @@ def world():
     return 0, 1
 
 
+def assert_identical_rng(what="resampling indices"):
+    """Multi-process runs draw the index matrices on every rank from numpy's GLOBAL stream and each rank keeps its
+    shard, which is only the reference's resample set if every rank's stream is in the same state (seed all ranks
+    alike; the common `seed + rank` idiom silently mixes shards of different streams).  One tiny all-reduce of a hash
+    of the state; raises on every rank when they differ."""
+    rank, size = world()
+    if size == 1:
+        return
+    import zlib
+    import numpy as np
+    import torch.distributed as dist
+    st = np.random.get_state(legacy=True)
+    h = (zlib.crc32(np.asarray(st[1], dtype=np.uint32).tobytes()) << 12) ^ int(st[2])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([h, -h], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hi, lo = int(t[0].item()), -int(t[1].item())
+    if hi != lo:
+        raise RuntimeError(
+            f"rank {rank}: numpy's global RNG state differs between the ranks, so the {what} drawn on each rank would "
+            "come from different streams and the sharded run would not be the reference's resample set.  Seed every "
+            "rank identically (np.random.seed(k), not k + rank) or pass perm_indices= / boot_indices= explicitly.")
+
+
 def shard(n, rank=None, size=None):
     """Contiguous [lo, hi) slice of range(n) owned by `rank`; sizes differ by at most one."""
     if rank is None:

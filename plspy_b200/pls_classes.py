@@ -145,7 +145,7 @@ class PLSBase(abc.ABC):
             perm_indices=self._engine_kwargs.get("perm_indices"),
             boot_indices=self._engine_kwargs.get("boot_indices"),
             engine=self._engine_kwargs.get("engine"), precision=self._engine_kwargs.get("precision", "fp64"),
-            rotate_method=self._engine_kwargs.get("rotate_method", 2), **kw)
+            rotate_method=self._engine_kwargs.get("rotate_method", 2), device=self._engine_kwargs.get("device"), **kw)
 
     def _split_half(self, Y, mctype, contrasts, **kw):
         """pls_classes.py:285-318 (identical block in every class)."""

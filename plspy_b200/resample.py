@@ -8,6 +8,13 @@ import numpy as np
 
 from . import class_functions
 
+
+def _same_stream_on_every_rank(what):
+    """Multi-process runs: every rank draws from numpy's global stream, which must be in the same state everywhere
+    (dist.assert_identical_rng); a no-op for a single process."""
+    from . import dist
+    dist.assert_identical_rng(what)
+
 # native generator (csrc/host_rng.cpp) continuing numpy's global MT19937 stream; set to False to force the
 # numpy path (tests compare the two)
 USE_NATIVE_RNG = True
@@ -99,6 +106,7 @@ def permutation_indices(pls_alg, nperm, cond_order, Y=None, bscan=None, Ybscan=N
     """Index vectors of all permutations (bootstrap_permutation.py:323-355).
     Returns (task (P x N) int32 or None, behaviour (P x Nb) int32 or None)."""
     co = np.asarray(cond_order)
+    _same_stream_on_every_rank("permutation indices")
     if USE_NATIVE_RNG and nperm > 0:
         out = _native_permutations(pls_alg, nperm, co, Y, Ybscan)
         if out is not None:
@@ -181,6 +189,7 @@ def bootstrap_indices(pls_alg, nboot, cond_order, Y=None, bscan=None, Ybscan=Non
     """Index vectors of all bootstraps (bootstrap_permutation.py:537-572).
     Returns (main (B x N) int32, behaviour-block (B x Nb) int32 or None)."""
     co = np.asarray(cond_order)
+    _same_stream_on_every_rank("bootstrap indices")
     if USE_NATIVE_RNG and nboot > 0:
         out = _native_bootstraps(pls_alg, nboot, co, Y, bscan, Ybscan)
         if out is not None:

@@ -42,6 +42,8 @@ def draw_split_indices(pls_alg, cond_order, num_split, n_rows):
     permutation(n_g) per group (:136 / :555), then per null split permutation(total subjects) (:271 / :692)
     followed by permutation(n_rows) (rows of X for task methods :282 / :703, rows of Y otherwise)."""
     co = np.asarray(cond_order)
+    from . import dist
+    dist.assert_identical_rng("split-half indices")
     real = [[np.random.permutation(co[g, 0]) for g in range(co.shape[0])] for _ in range(num_split)]
     nsub = n_rows // co.shape[1]
     null_subj, null_rows = [], []

@@ -69,6 +69,39 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _rng_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from plspy_b200 import dist as pd, resample
+        co = np.array([[4, 4, 4], [5, 5, 5]])
+        np.random.seed(11)                                   # identical streams: indices are drawn, identical everywhere
+        a = resample.bootstrap_indices("mct", 7, co)[0]
+        t = torch.from_numpy(a.astype(np.int64)); lo = t.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        same = bool((t == lo).all())
+        np.random.seed(11 + rank)                            # the seed + rank idiom: must be refused, on every rank
+        try:
+            resample.permutation_indices("mct", 3, co)
+            refused = False
+        except RuntimeError as e:
+            refused = "RNG state differs" in str(e)
+        with pd.local_only():                                # a rank working on its own: no collective, no check
+            assert pd.world() == (0, 1) and pd.shard(10) == (0, 10)
+            resample.permutation_indices("mct", 3, co)
+        assert pd.world() == (rank, world)
+        out[rank] = (same, refused)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rng_state_must_agree_across_ranks_world2():
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_rng_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert all(out[r] == (True, True) for r in range(world))
+
+
 def test_sharded_reduction_world2():
     world = 2
     mgr = mp.get_context("spawn").Manager()      # no fork() of this (multi-threaded) test process

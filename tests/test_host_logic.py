@@ -243,3 +243,19 @@ def test_confidence_interval_matches_the_elementwise_loop():
                     y = np.concatenate(([X.min()], X, [X.max()]))
                     np.testing.assert_allclose(lo[i, j], np.interp(conf[0] * 100, x, y), rtol=1e-12, atol=1e-14)
                     np.testing.assert_allclose(hi[i, j], np.interp(conf[1] * 100, x, y), rtol=1e-12, atol=1e-14)
+
+
+def test_lazy_debug_dict_behaves_like_the_reference_plain_dict():
+    """every read access sees the lazily computed entries (the reference returns a plain dict with all keys)"""
+    from plspy_b200.bootstrap_permutation import _LazyDebugDict
+    calls = []
+    d = _LazyDebugDict()
+    d["s_list"] = 1
+    d.set_lazy("indices", lambda: calls.append("i") or 2)
+    d.set_lazy("right_sv_sampled", lambda: calls.append("r") or 3)
+    assert len(d) == 3 and set(d) == {"s_list", "indices", "right_sv_sampled"} and "indices" in d
+    assert calls == []                                    # nothing computed by listing
+    assert d.get("right_sv_sampled") == 3 and d.get("missing", 7) == 7
+    assert dict(d) == {"s_list": 1, "indices": 2, "right_sv_sampled": 3}
+    assert sorted(d.values()) == [1, 2, 3] and dict(d.items())["indices"] == 2
+    assert sorted(calls) == ["i", "r"]                    # each lazy entry computed exactly once

@@ -1,5 +1,7 @@
 """Where does one pass of the bench workload spend its time?  Wraps every Engine method with host timestamps and
 CUDA events (development aid; run on the GPU box: PYTHONPATH=. python tools/phase_times.py [--precision tf32x3])."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import argparse, json, time
 import numpy as np, torch
 import bench

@@ -2,6 +2,8 @@
 
     PYTHONPATH=. python tools/profile_half_gram.py [windowed|dense] [splits]
 """
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import sys
 import numpy as np, torch
 from plspy_b200 import split_half_resampling as sh

@@ -48,8 +48,9 @@ lo_p, hi_p = pdist.shard(P); lo_b, hi_b = pdist.shard(B)
 np.random.seed(1234 + 5 + rank)
 t0 = time.perf_counter()
 ip = np.zeros((P, N), np.int32); ib = np.zeros((B, N), np.int32)
-ip[lo_p:hi_p] = resample.permutation_indices("mct", hi_p - lo_p, co)[0]
-ib[lo_b:hi_b] = resample.bootstrap_indices("mct", hi_b - lo_b, co)[0]
+with pdist.local_only():          # every rank draws its own shard from its own stream (seed + rank) on purpose
+    ip[lo_p:hi_p] = resample.permutation_indices("mct", hi_p - lo_p, co)[0]
+    ib[lo_b:hi_b] = resample.bootstrap_indices("mct", hi_b - lo_b, co)[0]
 t_idx = time.perf_counter() - t0
 ipd = torch.from_numpy(ip).to(dev); ibd = torch.from_numpy(ib).to(dev)
 out = {"config": f"cfg 5: mct 4 x 50 x 6 (N={N}) x {p} features, {P} perm + {B} boot over {world} GPU(s)",

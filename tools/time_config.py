@@ -1,4 +1,6 @@
 """Wall/CUDA-event timing of whole BASELINE configs through the public API (development aid)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import argparse, json, time
 import numpy as np, torch
 import plspy_b200

@@ -3,6 +3,8 @@
 
     PYTHONPATH=. python tools/time_half_gram.py [--splits 50]
 """
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import argparse, json
 import numpy as np, torch
 from plspy_b200 import split_half_resampling as sh

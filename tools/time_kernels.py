@@ -1,4 +1,6 @@
 """Quick CUDA-event timing of the individual kernels at a given shape (development aid)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import argparse, json, time
 import numpy as np, torch
 from plspy_b200.engine import Engine

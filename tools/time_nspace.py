@@ -2,6 +2,8 @@
 
     PYTHONPATH=. python tools/time_nspace.py
 """
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import json
 import numpy as np, torch
 from plspy_b200.engine import Engine
