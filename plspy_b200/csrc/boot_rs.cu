@@ -10,16 +10,35 @@
 // across the four stages.  Once per period the RS partial D fragments of a voxel group are exchanged through shared
 // memory (double-buffered, one named barrier per period and voxel group) and the warp with row-chunk 0 folds
 // (VS - pivot) into the running moments.
+//
+// L2 traffic: with the A fragments in registers an SM holds only 16 (RS = 4) or 32 (RS = 2) voxels, so every SM
+// re-reads the whole coefficient stream for very few voxels: 246 KB per 3.9 us period and SM = 9.3 TB/s over the chip
+// at N = 1200 -- the L2 cannot deliver that (ncu: 12 % of the warp samples wait for a stage to land, DMMA pipe 77 %).
+// The kernel therefore runs as thread-block CLUSTERS of CL (default 2) CTAs on adjacent voxel tiles that share
+// one coefficient stream: every CTA fetches 1/CL of each stage and MULTICASTS it into the shared memory of all CTAs
+// of the cluster (cp.async.bulk ... .multicast::cluster), each CTA's `full` barrier collecting the bytes of all CL
+// shares; a slot is refilled once every warp of every CTA of the cluster has drained it (remote mbarrier arrives).
 #include "common.cuh"
 
 namespace plsb {
 
-constexpr int RS_NSUB = 4;       // pipeline stages per period
+static int rs_nsub() { return 4; }       // pipeline stages per period
 
 struct RsPlan {
-    int Kp, nacc, nb, rs, nks, ck, nper, nstage, nsplit, per_per_split, vox;
+    int Kp, nacc, nb, rs, nks, ck, nsub, nper, nstage, nsplit, per_per_split, vox, cl;
     size_t stage_doubles, smem_bytes;
 };
+
+// CTAs per cluster.  Measured at N = 1200 (RS = 4), 1250 bootstraps x 10^6 voxels per GPU, TFLOP/s at (SM clock, board
+// power): no cluster 23.4-24.8 (1822 MHz under sw_power_cap, 1006 W) and 28.0 on a cool box; pairs 24.7-27.1 (1965 MHz,
+// 859 W); clusters of four 24.7 (1965 MHz, 681 W).  Multicast takes a third of the board power out (the L2 reads) but
+// the SM-side ingest of a stage stays on the critical path; pairs are the default.  PLSB200_RS_CLUSTER=1|2|4 overrides.
+static int rs_cluster_size(int rs) {
+    static const char* const env = getenv("PLSB200_RS_CLUSTER");
+    if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) return env[0] - '0';
+    (void)rs;
+    return 2;
+}
 
 static bool rs_plan(int N, int K, int R, int64_t p, RsPlan& b) {
     if (K < 1 || K > 24 || N <= 320 || R < 1) return false;
@@ -36,18 +55,19 @@ static bool rs_plan(int N, int K, int R, int64_t p, RsPlan& b) {
     int nks = (int)cdiv(cdiv(ksteps, b.rs), 8) * 8;      // buckets of 8 k-steps: 48, 56, 64, 72, 80
     if (nks < 48) nks = 48;
     if (nks > 80) return false;                          // N > 1280
-    b.nks = nks; b.ck = nks / RS_NSUB;
+    b.nks = nks; b.nsub = rs_nsub(); b.ck = nks / b.nsub;
     b.nper = (int)cdiv(R, b.nb);
     b.stage_doubles = (size_t)b.rs * b.ck * b.nacc * 32;
     b.vox = 8 * (8 / b.rs);
     const size_t extra = (size_t)(8 / b.rs) * 16 * b.Kp * 8 +
                          (size_t)2 * (8 / b.rs) * (b.rs - 1) * 64 * b.nacc * 8 + 256;
     int ns = (int)((227 * 1024 - extra) / (b.stage_doubles * 8));
-    if (ns > 6) ns = 6;
+    if (ns > 8) ns = 8;
     if (ns < 2) return false;
     b.nstage = ns;
     b.smem_bytes = ns * b.stage_doubles * 8 + extra;
-    const int64_t tiles = cdiv(p > 0 ? p : 1, b.vox);
+    b.cl = rs_cluster_size(b.rs);
+    const int64_t tiles = cdiv(cdiv(p > 0 ? p : 1, b.vox), b.cl) * b.cl;     // whole clusters
     const int nsm = num_sms();
     int best = 1; double best_cost = 1e30;
     for (int n = 1; n <= 8; ++n) {
@@ -66,7 +86,7 @@ static bool rs_plan(int N, int K, int R, int64_t p, RsPlan& b) {
 // s = (i % (4*nks))/4 -> sub = s / ck, s_in = s % ck ; q = i%4 ; lane = 4n + q
 __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restrict__ E, int N, int K,
                                                           const int32_t* __restrict__ idx, int Kp, int nacc, int nb,
-                                                          int rs, int nks, int ck, double* __restrict__ coef) {
+                                                          int rs, int nks, int ck, int nsub, double* __restrict__ coef) {
     extern __shared__ int ids[];          // E (N x K) stays in global memory: L1/L2-resident, read via __ldg
     const int r = blockIdx.x;
     for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
@@ -84,7 +104,7 @@ __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restr
             }
         const int rc = i / (4 * nks), s = (i % (4 * nks)) >> 2, q = i & 3;
         const int sub = s / ck, s_in = s % ck;
-        const size_t base = ((((size_t)per * RS_NSUB + sub) * rs + rc) * ck + s_in) * nacc;
+        const size_t base = ((((size_t)per * nsub + sub) * rs + rc) * ck + s_in) * nacc;
 #pragma unroll
         for (int k = 0; k < 24; ++k)
             if (k < K) {
@@ -94,14 +114,14 @@ __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restr
     }
 }
 
-template <int NKS, int NACC, int RS>
+template <int NKS, int NACC, int RS, int NSUB>
 __global__ void __launch_bounds__(256, 1)
 boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
                        const double* __restrict__ coef, int nper, int per_per_split, int nstage, int R, int Kp, int K,
-                       const double* __restrict__ pivot, double* __restrict__ osum, double* __restrict__ osumsq) {
+                       const double* __restrict__ pivot, double* __restrict__ osum, double* __restrict__ osumsq, int cl) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int NVG = 8 / RS;                    // voxel groups per CTA
-    constexpr int CK = NKS / RS_NSUB;              // k-steps per row chunk and stage
+    constexpr int CK = NKS / NSUB;              // k-steps per row chunk and stage
     constexpr int stage_doubles = RS * CK * NACC * 32;
     constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
     double* ring = reinterpret_cast<double*>(smraw);
@@ -116,31 +136,37 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
     const long long v = (long long)blockIdx.x * (NVG * 8) + vg * 8 + vr;
     const int per0 = blockIdx.y * per_per_split;
     const int per1 = min(nper, per0 + per_per_split);
-    const int nit = (per1 - per0) * RS_NSUB;       // pipeline stages of this CTA
+    const int nit = (per1 - per0) * NSUB;       // pipeline stages of this CTA
 
+    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8 * cl); }
         mbar_fence_init();
     }
-    __syncthreads();
+    if (cl > 1) cluster_sync_all(); else __syncthreads();      // every CTA's barriers exist before a peer touches them
+    // thread 0: this CTA's share (1 / cl) of stage `it`, delivered to every CTA of the cluster; the CTA's own `full`
+    // barrier expects the whole stage (its own share plus the peers' multicasts)
+    const uint32_t share = stage_bytes / (uint32_t)cl;
+    const uint16_t mask = (uint16_t)((1u << cl) - 1u);
     auto issue = [&](int it, int slot) {
         mbar_expect_tx(full + slot, stage_bytes);
-        const char* src = reinterpret_cast<const char*>(coef + ((size_t)per0 * RS_NSUB + it) * stage_doubles);
-        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+        const char* src = reinterpret_cast<const char*>(coef + ((size_t)per0 * NSUB + it) * stage_doubles) + crank * share;
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles) + crank * share;
 #pragma unroll 1
-        for (uint32_t off = 0; off < stage_bytes; off += 16384u)
-            bulk_g2s(dst + off, src + off, min(16384u, stage_bytes - off), full + slot);
+        for (uint32_t off = 0; off < share; off += 16384u) {
+            const uint32_t n = min(16384u, share - off);
+            if (cl > 1) bulk_g2s_multicast(dst + off, src + off, n, full + slot, mask);
+            else bulk_g2s(dst + off, src + off, n, full + slot);
+        }
     };
     if (tid == 0)
         for (int it = 0; it < min(nstage, nit); ++it) issue(it, it);
-    // Refills are issued by whichever warp is the LAST to drain a slot (a shared-memory counter per slot tells it so):
-    // stage j + nstage goes out at the earliest possible moment and nobody waits for anybody.  (Thread 0 waiting on
-    // the `empty` barrier before each of its own stages -- the scheme of boot_moments_kernel -- kept warp 0 in lock-step
-    // with the slowest warp of the CTA at every stage, four times per period here; probing the barrier without
-    // blocking at stage boundaries delayed the refills by up to a stage and was slower still: 24.6 vs 28.0 TFLOP/s.)
-    int* drained = reinterpret_cast<int*>(empty + nstage);     // [nstage]
-    if (tid < nstage) drained[tid] = 0;
-    __syncthreads();
+    // Refills: thread 0 (also a consumer: the register file holds exactly eight warps of resident fragments, there is no
+    // room for a producer warp) refills, at the start of each of its stages, the slot drained in the previous stage,
+    // after waiting for every warp of the cluster to have left it.  Measured alternatives at N = 1200 (TFLOP/s, same
+    // box): a non-blocking probe of the `empty` barrier at stage boundaries 24.6, also in mid-stage 22.8, refill by
+    // whichever warp drains the slot last 27.3, this scheme 28.0; stages of half the size (ring twice as deep)
+    // 19.9-22.7: what is on the critical path is the refill latency of a 61 KB stage, not lock-step between warps.
 
     double a[NKS];
 #pragma unroll
@@ -163,14 +189,23 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
     // stream in flight while the other exchanges / folds its accumulators at a period boundary
     if (warp >= 4) __nanosleep((unsigned)(CK * NACC * 8));
 
-    int slot = 0, it = 0;
-    uint32_t phase = 0;
+    int slot = 0, prev_slot = 0, it = 0;
+    uint32_t phase = 0, prev_phase = 0;
+    const uint32_t empty_base = smem_u32(empty);
     for (int per = per0; per < per1; ++per) {
         double d[NACC][2];
 #pragma unroll
         for (int j = 0; j < NACC; ++j) { d[j][0] = -piv[j][0]; d[j][1] = -piv[j][1]; }
 #pragma unroll
-        for (int sub = 0; sub < RS_NSUB; ++sub, ++it) {
+        for (int sub = 0; sub < NSUB; ++sub, ++it) {
+            if (tid == 0 && it > 0) {
+                const int nx = it - 1 + nstage;
+                if (nx < nit) {
+                    mbar_wait(empty + prev_slot, prev_phase);
+                    issue(nx, prev_slot);
+                }
+            }
+            __syncwarp();
             mbar_wait(full + slot, phase);
             // volatile: keeps the loads in program order (k-step major, chains round-robin), see boot_moments_kernel
             const volatile double* bs = ring + (size_t)slot * stage_doubles + (size_t)rc * CK * NACC * 32 + lane;
@@ -183,16 +218,12 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(empty + slot);
-                if (atomicAdd(drained + slot, 1) == 7) {        // this warp is the last of the eight: refill the slot
-                    drained[slot] = 0;
-                    if (it + nstage < nit) {
-                        mbar_wait(empty + slot, phase);          // (complete: orders the eight warps' reads before the copy)
-                        issue(it + nstage, slot);
-                    }
-                }
+            if (cl == 1) {
+                if (lane == 0) mbar_arrive(empty + slot);
+            } else if (lane < cl) {                                  // one arrive per CTA of the cluster
+                mbar_arrive_cluster(mapa_u32(empty_base + (uint32_t)slot * 8u, (uint32_t)lane));
             }
+            prev_slot = slot; prev_phase = phase;
             if (++slot == nstage) { slot = 0; phase ^= 1u; }
         }
         // combine the RS partial fragments of this voxel group, once per period
@@ -229,7 +260,7 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
             }
         }
     }
-    if (rc != 0) return;
+    if (rc == 0) {
     double* r1 = red + vg * (16 * Kp);
     double* r2 = r1 + 8 * Kp;
     for (int i = lane; i < 16 * Kp; i += 32) r1[i] = 0.0;
@@ -257,6 +288,9 @@ boot_moments_rs_kernel(const double* __restrict__ X, long long ldx, int N, long 
             o2[(vbase + rr) * K + k] = r2[rr * Kp + k];
         }
     }
+    }
+    // no CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers
+    if (cl > 1) cluster_sync_all();
 }
 
 __global__ void rs_moments_reduce_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int nsplit,
@@ -268,14 +302,22 @@ __global__ void rs_moments_reduce_kernel(const double* __restrict__ p1, const do
     sum[i] = a; sumsq[i] = b;
 }
 
-template <int NKS, int NACC, int RS>
+template <int NKS, int NACC, int RS, int NSUB>
 static int rs_launch(const RsPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R,
                      const double* pivot, double* o1, double* o2, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_rs_kernel<NKS, NACC, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_rs_kernel<NKS, NACC, RS, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)b.smem_bytes));
-    dim3 grid((unsigned)cdiv(p, b.vox), (unsigned)b.nsplit);
-    boot_moments_rs_kernel<NKS, NACC, RS><<<grid, 256, b.smem_bytes, st>>>(X, ldx, N, p, coef, b.nper, b.per_per_split,
-                                                                          b.nstage, R, b.Kp, K, pivot, o1, o2);
+    const unsigned gx = (unsigned)(cdiv(cdiv(p, b.vox), b.cl) * b.cl);           // whole clusters (surplus CTAs: v >= p)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, (unsigned)b.nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = b.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)b.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = b.cl > 1 ? 1 : 0;
+    const long long ldx_ll = (long long)ldx, p_ll = (long long)p;
+    PLSB_CUDA(cudaLaunchKernelEx(&cfg, boot_moments_rs_kernel<NKS, NACC, RS, NSUB>, X, ldx_ll, N, p_ll, coef, b.nper,
+                                 b.per_per_split, b.nstage, R, b.Kp, K, pivot, o1, o2, b.cl));
     PLSB_LAUNCH_CHECK("boot_moments_rs_kernel");
     return PLSB200_OK;
 }
@@ -284,11 +326,11 @@ template <int NACC, int RS>
 static int rs_dispatch_nks(const RsPlan& b, const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K,
                            int R, const double* pivot, double* o1, double* o2, cudaStream_t st) {
     switch (b.nks) {
-        case 48: return rs_launch<48, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        case 56: return rs_launch<56, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        case 64: return rs_launch<64, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        case 72: return rs_launch<72, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
-        case 80: return rs_launch<80, NACC, RS>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 48: return rs_launch<48, NACC, RS, 4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 56: return rs_launch<56, NACC, RS, 4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 64: return rs_launch<64, NACC, RS, 4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 72: return rs_launch<72, NACC, RS, 4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
+        case 80: return rs_launch<80, NACC, RS, 4>(b, X, N, p, ldx, coef, K, R, pivot, o1, o2, st);
         default: set_err("boot_moments_f64: no row-split kernel for nks=%d", b.nks); return PLSB200_EUNSUPPORTED;
     }
 }
@@ -306,7 +348,7 @@ static int rs_dispatch_nacc(const RsPlan& b, const double* X, int N, int64_t p, 
 size_t boot_rs_coef_bytes(int N, int K, int R) {
     RsPlan b;
     if (!rs_plan(N, K, R, 1, b)) return 0;
-    return (size_t)b.nper * RS_NSUB * b.stage_doubles * sizeof(double);
+    return (size_t)b.nper * b.nsub * b.stage_doubles * sizeof(double);
 }
 
 size_t boot_rs_workspace(int N, int64_t p, int K, int R) {
@@ -321,9 +363,9 @@ int boot_rs_pack(const double* E, int N, int K, const int32_t* idx, int R, doubl
         set_err("boot_coef_pack_f64: unsupported shape N=%d K=%d R=%d (need K<=24, N<=1280)", N, K, R);
         return PLSB200_EUNSUPPORTED;
     }
-    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * RS_NSUB * b.stage_doubles * sizeof(double), st));
+    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * b.nsub * b.stage_doubles * sizeof(double), st));
     size_t smem = (size_t)N * sizeof(int);
-    boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nacc, b.nb, b.rs, b.nks, b.ck, coef);
+    boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nacc, b.nb, b.rs, b.nks, b.ck, b.nsub, coef);
     PLSB_LAUNCH_CHECK("boot_rs_pack_kernel");
     return PLSB200_OK;
 }

@@ -238,30 +238,7 @@ struct TfArgs {
                            // empty hand-shake: wrong results, isolates contention from waiting), 2 = no producer at all
 };
 
-// ---- cluster helpers (CTA pair, cta_group::2)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-// Remote arrive with the default (release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) does: what the
-// barriers of this kernel order across the pair is asynchronous-proxy traffic (bulk copies into shared memory, tensor-core
-// reads of it, tensor-memory reads) that has already completed when the arrive is issued, so no cluster-scope
-// fence is needed -- .release.cluster / .acquire.cluster compile to MEMBAR.ALL.GPU + CCTL.IVALL per pipeline stage
-// and made the pair kernel 30% SLOWER than the single-CTA one.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
+// ---- cluster helpers: cluster_ctarank, cluster_sync_all, mapa_u32, mbar_arrive_cluster live in common.cuh
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // COLL: use of the tensor core's A-operand collector buffer -- 0 none, 1 fill (SASS A_KEEP: keep this A for the next MMA),
 // 2 lastuse (A_REUSE: take A from the collector instead of shared memory).  Of the three products of a k-step two share

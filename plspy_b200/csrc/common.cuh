@@ -134,6 +134,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// ---- thread-block clusters: rank, cluster barrier, remote mbarrier arrive, multicast bulk copy ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// Remote arrive with the default (release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) does: what the
+// barriers of these kernels order across CTAs is asynchronous-proxy traffic (bulk copies into shared memory and
+// reads of it that have completed when the arrive is issued), so no cluster-scope fence is needed --
+// .release.cluster / .acquire.cluster compile to MEMBAR.ALL.GPU + CCTL.IVALL per pipeline stage.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// global -> the SAME shared-memory offset in every CTA of `cta_mask`; each destination CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes written into that CTA.  One L2 read feeds all the destination SMs.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
 // ---- Ampere-style cp.async with zero fill (SASS LDGSTS) ----
 template <int BYTES>
 __device__ __forceinline__ void cp_async_zfill(void* dst_smem, const void* src_gmem, int src_bytes) {

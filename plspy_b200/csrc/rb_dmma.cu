@@ -23,7 +23,7 @@ namespace plsb {
 constexpr int RD_MAXKS = 96;
 
 struct RdPlan {
-    int nks, nblk, kcp, npass, nstage, warps;
+    int nks, nblk, kcp, npass, nstage, warps;   // warps: template bucket (8 or 16) = upper bound of the launch
     size_t stage_doubles;        // packed coefficients + weights of one bootstrap and one pass
     size_t smem_bytes;
     int krow[RD_MAXKS * 4];      // k-step slot -> row of Xc (-1 = padding)
@@ -56,7 +56,7 @@ static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, 
     r.stage_doubles = (size_t)r.nks * r.nblk * 32 + (size_t)r.nks * 4;
     r.warps = r.nks <= 32 ? 16 : 8;
     // weight ring (4 slots), block sizes, running moments, per-warp scale / moment tables, barriers
-    const size_t fixed = ((size_t)4 * r.nks * 4 + 16 + 2 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 24) * sizeof(double) + 256;
+    const size_t fixed = ((size_t)4 * r.nks * 4 + 16 + 3 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 24) * sizeof(double) + 256;
     const size_t coef_bytes = (size_t)r.nks * r.nblk * 32 * sizeof(double);
     int ns = (int)((225 * 1024 - fixed) / coef_bytes);
     if (ns > 4) ns = 4;
@@ -100,7 +100,7 @@ struct RdArgs {
     double* VSt;       // [nbt][kcp][p]  (may be NULL when T is not wanted)
     double* Npart;     // [nbt][kcp][tiles*8]
     long long p;
-    int Kfull, k0, kc, nbt, npass, pass, nstage, ncell;
+    int Kfull, k0, kc, nbt, npass, pass, nstage, ncell, nwarps;
     uint32_t cend[3];
 };
 
@@ -119,7 +119,7 @@ __device__ __forceinline__ double rd_scale(double m1, double m2, double n) {
 // twice the warps per scheduler to hide the serial phases between the DMMA bursts).
 template <int NKS, int NBLK, int W>
 __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
-    constexpr int RD_WARPS = W, RD_THREADS = W * 32, RD_VOX = W * 8;
+    constexpr int RD_WARPS = W, RD_THREADS = W * 32;
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int coef_doubles = NKS * NBLK * 32;                 // B fragments of one bootstrap and pass
     constexpr int w_doubles = NKS * 4;                            // its multiplicity weights, k-step order
@@ -130,22 +130,24 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
     double* wring = ring + (size_t)a.nstage * coef_doubles;       // [WSLOTS][w_doubles]
     double* celln = wring + WSLOTS * w_doubles;                   // [RD_MAXCELL] rows per cell (negative: unit cell)
     double* acc = celln + RD_MAXCELL;                             // [2][NBLK*2][RD_THREADS] running moments
-    double* tabs = acc + 2 * NBLK * 2 * RD_THREADS;               // per warp: scale[16][8], then (m1, m2)[16][8]
+    double* pvs = acc + 2 * NBLK * 2 * RD_THREADS;                // [NBLK*2][RD_THREADS] pivot of this thread's elements
+    double* tabs = pvs + NBLK * 2 * RD_THREADS;                   // per warp: scale[16][8], then (m1, m2)[16][8]
     uint64_t* full = reinterpret_cast<uint64_t*>(tabs + RD_WARPS * RD_MAXCELL * 24);
     uint64_t* empty = full + a.nstage;
     uint64_t* wfull = empty + a.nstage;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = lane & 3, vr = lane >> 2;
-    const long long v = (long long)blockIdx.x * RD_VOX + warp * 8 + vr;
+    const int nwarps = a.nwarps;                                  // warps launched (<= W, see rd_balanced_warps)
+    const long long v = (long long)blockIdx.x * (nwarps * 8) + warp * 8 + vr;
     const bool ok = v < a.p;
 
     if (tid == 0) {
-        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, RD_WARPS); }
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nwarps); }
         for (int s = 0; s < WSLOTS; ++s) mbar_init(wfull + s, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < RD_MAXCELL; i += RD_THREADS) celln[i] = i < a.ncell ? a.celln[i] : 0.0;
+    for (int i = tid; i < RD_MAXCELL; i += nwarps * 32) celln[i] = i < a.ncell ? a.celln[i] : 0.0;
     __syncthreads();
 
     const size_t bstride = (size_t)a.npass * pack_doubles;        // doubles between consecutive bootstraps
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
     // running moments live in shared memory (one slot per thread and fragment element): registers are for X
     double* my1 = acc + tid;
     double* my2 = acc + NBLK * 2 * RD_THREADS + tid;
+    double* myp = pvs + tid;
 #pragma unroll
     for (int j = 0; j < NBLK; ++j)
 #pragma unroll
@@ -185,6 +188,9 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
             const bool live = ok && c < a.kc;
             my1[(2 * j + e) * RD_THREADS] = live ? a.sum[v * a.Kfull + a.k0 + c] : 0.0;
             my2[(2 * j + e) * RD_THREADS] = live ? a.sumsq[v * a.Kfull + a.k0 + c] : 0.0;
+            // (the pivot is the same for every bootstrap: read once -- as a per-bootstrap __ldg its L2 latency sat on
+            // the fold's critical path, 5 % of the warp samples)
+            myp[(2 * j + e) * RD_THREADS] = (live && a.pivot) ? __ldg(a.pivot + v * a.Kfull + a.k0 + c) : 0.0;
         }
     double* sct = tabs + warp * (RD_MAXCELL * 24);                // scale[cell][voxel] of the current bootstrap
     double* mt = sct + RD_MAXCELL * 8;                            // (m1, m2)[cell][voxel] of the next one
@@ -282,8 +288,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
             for (int e = 0; e < 2; ++e) {
                 const int c = 8 * j + 2 * q + e;
                 const double val = ok ? vs[j][e] : 0.0;
-                const double pv = (ok && a.pivot && c < a.kc) ? __ldg(a.pivot + v * a.Kfull + a.k0 + c) : 0.0;
-                const double dd = val - pv;
+                const double dd = val - myp[(2 * j + e) * RD_THREADS];
                 my1[(2 * j + e) * RD_THREADS] += dd;
                 my2[(2 * j + e) * RD_THREADS] = fma(dd, dd, my2[(2 * j + e) * RD_THREADS]);
                 double n2 = val * val;
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                 n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
                 n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
                 if (vr == 0)
-                    a.Npart[((size_t)bb * (8 * NBLK) + c) * ((size_t)gridDim.x * RD_WARPS) + blockIdx.x * RD_WARPS + warp] = n2;
+                    a.Npart[((size_t)bb * (8 * NBLK) + c) * ((size_t)gridDim.x * nwarps) + blockIdx.x * nwarps + warp] = n2;
                 if (a.VSt && ok) a.VSt[((size_t)bb * (8 * NBLK) + c) * a.p + v] = val;
             }
         if (has_next) scales();                                   // scales of bootstrap bb+1 from its moments
@@ -424,9 +429,15 @@ __global__ void rd_latent_reduce_kernel(const double* __restrict__ part, int nti
 
 struct RdLayout {
     size_t off_krow, off_celln, off_pack, off_vst, off_npart, off_gpart, total;
-    int ntile, nta, ntb, nsplit;
+    int ntile, nta, ntb, nsplit, nwarps;
     long long chunk;
 };
+
+// Warps (= groups of 8 voxels) per CTA actually launched.  Fewer warps than the kernel's bucket would fill the waves of
+// SMs more evenly (50 000 voxels are 391 CTAs of 16 warps = 2.64 waves, 569 CTAs of 11 warps = 3.84), but the kernel
+// is latency-bound, not pipe-bound: with 11 instead of 16 (5 instead of 8) warps per SM it ran 8 % (44 %) SLOWER
+// (cfg 2: 21.5 -> 23.2 ms, cfg 4: 55.6 -> 80.0 ms per analysis).  The full bucket is used.
+static int rd_balanced_warps(int maxw, int64_t) { return maxw; }
 
 static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_t) {
     RdLayout L;
@@ -435,9 +446,10 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     L.off_krow = o; o = al(o + (size_t)r.nks * 4 * sizeof(int));
     L.off_celln = o; o = al(o + 16 * sizeof(double));
     L.off_pack = o; o = al(o + (size_t)nbt * r.npass * r.stage_doubles * sizeof(double));
-    L.ntile = (int)cdiv(p, r.warps * 8);
+    L.nwarps = rd_balanced_warps(r.warps, p);
+    L.ntile = (int)cdiv(p, L.nwarps * 8);
     L.off_vst = o; if (want_t) o = al(o + (size_t)nbt * r.kcp * p * sizeof(double));
-    L.off_npart = o; o = al(o + (size_t)L.ntile * r.warps * nbt * r.kcp * sizeof(double));
+    L.off_npart = o; o = al(o + (size_t)L.ntile * L.nwarps * nbt * r.kcp * sizeof(double));
     L.nta = (int)cdiv(N, GN_T); L.ntb = (int)cdiv((int64_t)nbt * r.kcp, GN_T);
     const int64_t nk = cdiv(p, GN_KC);
     int64_t ns = cdiv(4LL * num_sms(), (int64_t)L.nta * L.ntb);
@@ -454,7 +466,7 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
 template <int NKS, int NBLK, int W>
 static int launch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
     PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
-    rb_vs_kernel<NKS, NBLK, W><<<ntile, W * 32, r.smem_bytes, st>>>(a);
+    rb_vs_kernel<NKS, NBLK, W><<<ntile, a.nwarps * 32, r.smem_bytes, st>>>(a);
     PLSB_LAUNCH_CHECK("rb_vs_kernel");
     return PLSB200_OK;
 }
@@ -528,7 +540,7 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
         a.Xc = Xc; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
         a.VSt = d_vst; a.Npart = d_npart; a.p = p; a.Kfull = K; a.k0 = pass * r.kcp;
         a.kc = K - a.k0 < r.kcp ? K - a.k0 : r.kcp;
-        a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell;
+        a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell; a.nwarps = L.nwarps;
         a.cend[0] = r.cend[0]; a.cend[1] = r.cend[1]; a.cend[2] = r.cend[2];
         int rc;
         switch (r.nblk) {
@@ -538,7 +550,7 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
         }
         if (rc != PLSB200_OK) return rc;
         rd_norm_reduce_kernel<<<(unsigned)cdiv((int64_t)nbt * a.kc * 32, 256), 256, 0, st>>>(
-            d_npart, L.ntile * r.warps, nbt, r.kcp, a.kc, K, a.k0, nrm2 + (size_t)b0 * K);
+            d_npart, L.ntile * L.nwarps, nbt, r.kcp, a.kc, K, a.k0, nrm2 + (size_t)b0 * K);
         PLSB_LAUNCH_CHECK("rd_norm_reduce_kernel");
         if (want_t) {
             const size_t smem = (size_t)2 * GN_STAGES * GN_T * GN_STR * sizeof(double);

@@ -179,6 +179,9 @@ CASES = [
     ("rb_bal", "rb", (6, 6), 2, 64, dict(nb=2, seed=9, nsplit=5, lv=2)),
     ("rb_unbal", "rb", (7, 5), 3, 72, dict(nb=3, seed=10)),
     ("csb_perm", "csb", (6, 6), 2, 64, dict(nb=2, L=2, seed=11, nboot=0, nsplit=5, lv=1)),
+    # csb WITH bootstraps: the reference only survives its confidence-interval step when the contrast matrix is
+    # square (lvcorrs_orig = lvintercorrs is L x L, LVcorr is K' x L: pls_classes.py:1158, bootstrap_permutation.py:725)
+    ("csb_square", "csb", (6, 6), 2, 64, dict(nb=2, L=8, seed=15)),
     ("mb_bscan", "mb", (6, 6), 3, 72, dict(nb=2, bscan=(0, 2), seed=12, nsplit=5, lv=2)),
     ("mb_full", "mb", (5, 7), 2, 64, dict(nb=2, seed=13, mctype=1)),
     ("cmb_full", "cmb", (6, 6), 2, 64, dict(nb=2, L=3, seed=14, nsplit=4, lv=1)),

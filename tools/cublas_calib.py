@@ -1,7 +1,9 @@
 """Calibration only (not the product path): cuBLAS FP64 / TF32 / FP32 GEMM ceilings on this B200,
 used as the FP64/TF32 roofline denominators that MEASURED_PEAKS.json does not carry."""
-import json, sys, time
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from tools._clocks import Clocks
 
 def bench(dtype, n, tf32=False, reps=10, sustained_s=0.0):
     torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -17,6 +19,11 @@ def bench(dtype, n, tf32=False, reps=10, sustained_s=0.0):
         best = min(best, e0.elapsed_time(e1))
     out = {"burst_tflops": 2 * n ** 3 / best * 1e-9}
     if sustained_s > 0:
+        clk = None
+        try:
+            clk = Clocks(0); clk.start()
+        except Exception:  # noqa: BLE001
+            pass
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.time(); k = 0
         e0.record()
@@ -26,6 +33,7 @@ def bench(dtype, n, tf32=False, reps=10, sustained_s=0.0):
             torch.cuda.synchronize()
         e1.record(); torch.cuda.synchronize()
         out["sustained_tflops"] = 2 * n ** 3 * k / e0.elapsed_time(e1) * 1e-9
+        out["clocks_during_sustained"] = clk.summary() if clk is not None else None
     return out
 
 if __name__ == "__main__":

@@ -55,10 +55,18 @@ t_idx = time.perf_counter() - t0
 ipd = torch.from_numpy(ip).to(dev); ibd = torch.from_numpy(ib).to(dev)
 out = {"config": f"cfg 5: mct 4 x 50 x 6 (N={N}) x {p} features, {P} perm + {B} boot over {world} GPU(s)",
        "index_generation_s_per_rank": t_idx}
+from tools._clocks import Clocks
+
 modes = ["fp64", "tf32x3"] if a.precision == "both" else [a.precision]
 for mode in modes:
     times = []
+    clk = None
     for rep in range(2):
+        if rep == 1 and rank == 0:
+            try:
+                clk = Clocks(local); clk.start()
+            except Exception:
+                clk = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -79,7 +87,7 @@ for mode in modes:
         kms = eng.kernel_ms("boot_moments")
         del eng
     nb_local = hi_b - lo_b
-    out[mode] = {"seconds": times[-1] * 1e-3, "first_call_seconds": times[0] * 1e-3,
+    out[mode] = {"clocks": clk.summary() if clk is not None else None, "seconds": times[-1] * 1e-3, "first_call_seconds": times[0] * 1e-3,
                  "resamples_per_s": (P + B) / (times[-1] * 1e-3),
                  "boot_moments_ms_rank0": sum(kms), "boot_moments_algorithmic_tflops_rank0":
                      2.0 * p * N * len(s) * nb_local / (sum(kms) * 1e-3) * 1e-12 if kms else None,
