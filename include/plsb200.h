@@ -62,6 +62,11 @@ int plsb200_copy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t
 size_t plsb200_gram_f64_workspace(int N, int64_t p);
 int plsb200_gram_f64(const double* X, int N, int64_t p, int64_t ldx, double* G,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same for the row stack [X1; X2] ((N1 + N2) x p) without materialising it: the multiblock methods need the Gram
+ * matrix of [X; Zb] (class_functions.py:454-516 through N-space quadratic forms).  Workspace:
+ * plsb200_gram_f64_workspace(N1 + N2, p).                                                                      */
+int plsb200_gram_stacked_f64(const double* X1, int N1, int64_t ld1, const double* X2, int N2, int64_t ld2, int64_t p,
+                             double* G, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- latent projection XL = X . V (N x K); replaces class_functions._compute_X_latents
  * (class_functions.py:165-182) as used for U_hat (bootstrap_permutation.py:617).
@@ -180,7 +185,10 @@ int plsb200_rb_coef_f64(const double* Y, int N, int nb, const int32_t* idx, int 
                         int ncell, const double* U, int Kc, int scatter, double* Q, double* W, double* Yz,
                         void* stream);
 size_t plsb200_rb_boot_f64_workspace(int N, int64_t p, int K, int nbt);
-int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
+ /* (the data matrix of rb_boot may be given as two row segments: rows [0, n1) = Xc (row stride p), rows [n1, N) = Xc2
+  * (row stride ld2); Xc2 == NULL: all N rows in Xc.  The multiblock bootstrap passes [Xcb; X] this way.)          */
+int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Xc2, int n1, int64_t ld2, const double* Q,
+                        const double* W, int K, int b0,
                         int nbt, const int32_t* cell_start, int ncell, int unit_cells, const double* pivot,
                         double* sum, double* sumsq, double* T, double* nrm2, void* workspace,
                         size_t workspace_bytes, void* stream);
@@ -191,7 +199,8 @@ int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, con
  * streams packed coefficients like the K4 kernel; the latent products T = Xc . VS are a split-K DMMA GEMM.     */
 size_t plsb200_rb_boot_dmma_f64_workspace(int N, int64_t p, int K, int nbt, const int32_t* cell_start_host,
                                           int ncell, int unit_cells, int want_t);
-int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
+int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Xc2, int n1, int64_t ld2,
+                             const double* Q, const double* W, int K, int b0,
                              int nbt, const int32_t* cell_start_host, int ncell, int unit_cells, const double* pivot,
                              double* sum, double* sumsq, double* T, double* nrm2, void* workspace,
                              size_t workspace_bytes, void* stream);

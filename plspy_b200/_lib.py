@@ -39,6 +39,8 @@ SIGNATURES = {
     "plsb200_copy2d_h2d": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "plsb200_gram_f64_workspace": (c_size_t, [c_int, c_int64]),
     "plsb200_gram_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_void_p, c_size_t, c_void_p]),
+    "plsb200_gram_stacked_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_int, c_int64, c_int64, c_double_p,
+                                         c_void_p, c_size_t, c_void_p]),
     "plsb200_xv_f64_workspace": (c_size_t, [c_int, c_int64, c_int]),
     "plsb200_xv_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_double_p, c_void_p,
                                c_size_t, c_void_p]),
@@ -81,11 +83,13 @@ SIGNATURES = {
     "plsb200_rb_coef_f64": (c_int, [c_double_p, c_int, c_int, c_int32_p, c_int, c_int32_p, c_int, c_double_p, c_int,
                                     c_int, c_double_p, c_double_p, c_double_p, c_void_p]),
     "plsb200_rb_boot_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),
-    "plsb200_rb_boot_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_double_p, c_int, c_int, c_int,
+    "plsb200_rb_boot_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_int, c_int64, c_double_p, c_double_p, c_int,
+                                    c_int, c_int,
                                     c_int32_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                     c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_rb_boot_dmma_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int]),
-    "plsb200_rb_boot_dmma_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_double_p, c_int, c_int, c_int,
+    "plsb200_rb_boot_dmma_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_int, c_int64, c_double_p, c_double_p,
+                                         c_int, c_int, c_int,
                                          c_void_p, c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                          c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_rb_lvcorr_f64": (c_int, [c_double_p, c_double_p, c_double_p, c_int32_p, c_int, c_int, c_int, c_int,

@@ -153,10 +153,10 @@ def _behaviour_state(eng, cells):
 
 
 def _multiblock_state(eng, cond_order, bscan, keep_zb=False):
-    """Per-engine cache for mb/cmb: the bscan rows of X block-centred (Xcb) and z-scored (Zb), the stacked
-    matrices W1 = [X; Zb] (permutations, with its Gram matrix) and W2 = [Xcb; X] (bootstraps), and the
+    """Per-engine cache for mb/cmb: the bscan rows of X block-centred (Xcb) and z-scored (Zb), the Gram matrix Gw
+    of the row stack W1 = [X; Zb] (permutations; formed from the two matrices, the stack is never built) and the
     column maps of the multiblock row order (per group: C task rows, then |bscan|*nb behaviour rows,
-    class_functions.py:496-514)."""
+    class_functions.py:496-514).  The bootstraps work on the stack W2 = [Xcb; X], likewise as two row segments."""
     co = np.asarray(cond_order)
     key = ("mb", tuple(co.reshape(-1).tolist()), tuple(bscan))
     st = getattr(eng, "_multiblock", None)
@@ -167,12 +167,11 @@ def _multiblock_state(eng, cond_order, bscan, keep_zb=False):
     cells_b = _cell_offsets(co[:, bscan])
     Xb = eng.X.index_select(0, torch.as_tensor(rows_b, device=eng.device))
     Xcb, Zb = eng.cell_standardize(cells_b, M=Xb)
-    W1 = torch.cat([eng.X, Zb], dim=0)
     st = {"key": key, "rows_b": rows_b, "cells_b": cells_b, "Xcb": Xcb, "Nb": int(Xb.shape[0]),
-          "Gw": eng.gram_of(W1), "W2": torch.cat([Xcb, eng.X], dim=0)}
+          "Gw": eng.gram_stacked(eng.X, Zb)}
     if keep_zb:         # the device-side original analysis projects on Zb once more (device_analysis.multiblock)
         st["Zb"] = Zb
-    del W1, Zb, Xb
+    del Zb, Xb
     eng._multiblock = st
     return st
 
@@ -213,8 +212,7 @@ def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast,
     C0 = np.zeros((N + Nb, K))
     C0[:N, tcol] = Lop.T
     C0[N:, bcol] = class_functions._behaviour_coefficients(Ybscan, np.asarray(cond_order)[:, list(bscan)])
-    C0 = eng.to_device(C0, torch.float64)
-    raw_sq = float(((st["Gw"] @ C0) * C0).sum())
+    raw_sq = float(eng.nspace_coef(st["Gw"], eng.to_device(C0[None], torch.float64))[0].sum())   # sum_k C0_k^T Gw C0_k
     org_s = np.sqrt(s ** 2 / np.sum(s ** 2) * raw_sq)
     totcov_org = _stepdown_tail(org_s)
     Ucoef = np.asarray(U, dtype=float) if contrast is None else class_functions._normalize(
@@ -289,7 +287,7 @@ def _boot_multiblock(eng, U, s, V, cond_order, mctype, niter, pls_alg, contrast,
     C2 = eng.coef_project(C1, d2row, Ucoef)                                         # R x (Nb+N) x Kc
     Wfull = torch.cat([Wb, torch.zeros(R, N, dtype=torch.float64, device=dev)], dim=1)
     cells2 = np.concatenate([st["cells_b"], [Nb + N]]).astype(np.int32)
-    s1, s2, T, nrm2 = eng.rb_boot(st["W2"], C2, Wfull, cells2, pivot=numer, unit_cells=1)   # pass 2
+    s1, s2, T, nrm2 = eng.rb_boot(st["Xcb"], C2, Wfull, cells2, pivot=numer, unit_cells=1, X2=eng.X)   # pass 2
     dist.allreduce_packed_([s1, s2])
     std_errs, boot_ratios = eng.boot_finalize(s1, s2, niter, numer=numer)
     LV = eng.rb_lvcorr(T[:, :Nb, :].contiguous(), nrm2, Yz, ib, st["cells_b"], nb)  # (:650, :674)

@@ -45,7 +45,8 @@ static GramPlan gram_plan(int N, int64_t p) {
 
 template <int VEC>  // doubles per cp.async (2 when rows are 16-B aligned, else 1)
 __global__ void __launch_bounds__(GTHREADS) gram_partial_kernel(const double* __restrict__ X, int N, long long p,
-                                                               long long ldx, long long chunk, int ntile,
+                                                               long long ldx, const double* __restrict__ X2, int n1,
+                                                               long long ld2, long long chunk, int ntile,
                                                                double* __restrict__ part) {
     extern __shared__ __align__(16) double sm[];
     // pair index -> (ti, tj) with tj >= ti
@@ -66,6 +67,9 @@ __global__ void __launch_bounds__(GTHREADS) gram_partial_kernel(const double* __
     double* As = sm;                            // [GSTAGES][GT][GSTR]
     double* Bs = sm + GSTAGES * GT * GSTR;      // same shape (unused on diagonal tiles)
 
+    // rows [0, n1) live in X, rows [n1, N) in X2 (the Gram matrix of the stack [X; X2] without materialising it;
+    // n1 == N: a single matrix)
+    auto rowp = [&](int row) { return row < n1 ? X + (long long)row * ldx : X2 + (long long)(row - n1) * ld2; };
     auto load_stage = [&](int st, int kt) {
         const long long vb = v0 + (long long)kt * GKC;
         constexpr int CH = GKC / VEC;           // chunks per row
@@ -76,13 +80,13 @@ __global__ void __launch_bounds__(GTHREADS) gram_partial_kernel(const double* __
             {
                 const int row = ti * GT + r;
                 const int nb = row < N ? (int)left * 8 : 0;
-                const double* src = nb ? X + (long long)row * ldx + v : X;
+                const double* src = nb ? rowp(row) + v : X;
                 cp_async_zfill<VEC * 8>(As + (st * GT + r) * GSTR + cc, src, nb);
             }
             if (!diag) {
                 const int row = tj * GT + r;
                 const int nb = row < N ? (int)left * 8 : 0;
-                const double* src = nb ? X + (long long)row * ldx + v : X;
+                const double* src = nb ? rowp(row) + v : X;
                 cp_async_zfill<VEC * 8>(Bs + (st * GT + r) * GSTR + cc, src, nb);
             }
         }
@@ -165,30 +169,44 @@ extern "C" size_t plsb200_gram_f64_workspace(int N, int64_t p) {
     return (size_t)g.nsplit * g.npair * GT * GT * sizeof(double);
 }
 
-extern "C" int plsb200_gram_f64(const double* X, int N, int64_t p, int64_t ldx, double* G, void* workspace,
-                                size_t workspace_bytes, void* stream) {
-    PLSB_CHECK_ARG(X && G && workspace, "gram_f64: null pointer");
-    PLSB_CHECK_ARG(N > 0 && p > 0 && ldx >= p, "gram_f64: bad shape N=%d p=%lld ldx=%lld", N, (long long)p,
-                   (long long)ldx);
+static int gram_launch(const double* X, int n1, int64_t ldx, const double* X2, int n2, int64_t ld2, int64_t p, double* G,
+                       void* workspace, size_t workspace_bytes, void* stream, const char* what) {
+    const int N = n1 + n2;
     GramPlan g = gram_plan(N, p);
     size_t need = (size_t)g.nsplit * g.npair * GT * GT * sizeof(double);
     if (workspace_bytes < need) {
-        set_err("gram_f64: workspace %zu < %zu bytes", workspace_bytes, need);
+        set_err("%s: workspace %zu < %zu bytes", what, workspace_bytes, need);
         return PLSB200_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * GSTAGES * GT * GSTR * sizeof(double);
-    const bool vec2 = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (ldx % 2 == 0);
+    const bool vec2 = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (ldx % 2 == 0) &&
+                      (n2 == 0 || (((reinterpret_cast<uintptr_t>(X2) & 15) == 0) && (ld2 % 2 == 0)));
     dim3 grid(g.npair, g.nsplit);
     if (vec2) {
         PLSB_CUDA(cudaFuncSetAttribute(gram_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_partial_kernel<2><<<grid, GTHREADS, smem, st>>>(X, N, p, ldx, g.chunk, g.ntile, (double*)workspace);
+        gram_partial_kernel<2><<<grid, GTHREADS, smem, st>>>(X, N, p, ldx, X2, n1, ld2, g.chunk, g.ntile, (double*)workspace);
     } else {
         PLSB_CUDA(cudaFuncSetAttribute(gram_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_partial_kernel<1><<<grid, GTHREADS, smem, st>>>(X, N, p, ldx, g.chunk, g.ntile, (double*)workspace);
+        gram_partial_kernel<1><<<grid, GTHREADS, smem, st>>>(X, N, p, ldx, X2, n1, ld2, g.chunk, g.ntile, (double*)workspace);
     }
     PLSB_LAUNCH_CHECK("gram_partial_kernel");
     gram_reduce_kernel<<<g.npair, 256, 0, st>>>((const double*)workspace, g.npair, g.nsplit, g.ntile, N, G);
     PLSB_LAUNCH_CHECK("gram_reduce_kernel");
     return PLSB200_OK;
+}
+
+extern "C" int plsb200_gram_f64(const double* X, int N, int64_t p, int64_t ldx, double* G, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    PLSB_CHECK_ARG(X && G && workspace, "gram_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && p > 0 && ldx >= p, "gram_f64: bad shape N=%d p=%lld ldx=%lld", N, (long long)p,
+                   (long long)ldx);
+    return gram_launch(X, N, ldx, nullptr, 0, 0, p, G, workspace, workspace_bytes, stream, "gram_f64");
+}
+
+extern "C" int plsb200_gram_stacked_f64(const double* X1, int N1, int64_t ld1, const double* X2, int N2, int64_t ld2,
+                                        int64_t p, double* G, void* workspace, size_t workspace_bytes, void* stream) {
+    PLSB_CHECK_ARG(X1 && X2 && G && workspace, "gram_stacked_f64: null pointer");
+    PLSB_CHECK_ARG(N1 > 0 && N2 > 0 && p > 0 && ld1 >= p && ld2 >= p, "gram_stacked_f64: bad shape");
+    return gram_launch(X1, N1, ld1, X2, N2, ld2, p, G, workspace, workspace_bytes, stream, "gram_stacked_f64");
 }

@@ -121,6 +121,7 @@ constexpr int RB_VCH = 32;
 
 template <int KC>
 __global__ void __launch_bounds__(RB_VT) rb_boot_kernel(const double* __restrict__ Xc, int N, long long p,
+                                                       const double* __restrict__ Xc2, int n1, long long ld2,
                                                        const double* __restrict__ Q, const double* __restrict__ W,
                                                        int Kq, int k0, int kc, int b0, int nbt,
                                                        const int32_t* __restrict__ cell_start, int ncell,
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(RB_VT) rb_boot_kernel(const double* __restrict
 #pragma unroll
             for (int k = 0; k < KC; ++k) P[k] = 0.0;
             for (int i = s; i < e; ++i) {
-                const double x = ok ? __ldg(Xc + (long long)i * p + v) : 0.0;
+                // rows [0, n1) of the data matrix live in Xc, rows [n1, N) in Xc2 (n1 == N: a single matrix)
+                const double x = ok ? __ldg((i < n1 ? Xc + (long long)i * p : Xc2 + (long long)(i - n1) * ld2) + v) : 0.0;
                 const double wx = Ws[i] * x;
                 m1 += wx;
                 m2 = fma(wx, x, m2);
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(RB_VT) rb_boot_kernel(const double* __restrict
             for (int i = tid; i < N * RB_VCH; i += RB_VT) {
                 const int row = i / RB_VCH, j = i % RB_VCH;
                 const long long vv = v0 + ch * RB_VCH + j;
-                Xs[row * (RB_VCH + 1) + j] = vv < p ? __ldg(Xc + (long long)row * p + vv) : 0.0;
+                Xs[row * (RB_VCH + 1) + j] =
+                    vv < p ? __ldg((row < n1 ? Xc + (long long)row * p : Xc2 + (long long)(row - n1) * ld2) + vv) : 0.0;
             }
             __syncthreads();
 #pragma unroll
@@ -522,13 +525,16 @@ extern "C" size_t plsb200_rb_boot_f64_workspace(int N, int64_t p, int K, int nbt
     return ntile * nbt * ((size_t)N * K + K) * sizeof(double);
 }
 
-extern "C" int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K, int b0,
+extern "C" int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const double* Xc2, int n1, int64_t ld2,
+                                   const double* Q, const double* W, int K, int b0,
                                    int nbt, const int32_t* cell_start, int ncell, int unit_cells, const double* pivot,
                                    double* sum,
                                    double* sumsq, double* T, double* nrm2, void* workspace, size_t workspace_bytes,
                                    void* stream) {
     PLSB_CHECK_ARG(Xc && Q && W && cell_start && sum && sumsq && T && nrm2 && workspace, "rb_boot_f64: null pointer");
     PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && nbt > 0 && ncell > 0, "rb_boot_f64: bad shape");
+    if (Xc2 == nullptr) { n1 = N; ld2 = p; }
+    PLSB_CHECK_ARG(n1 > 0 && n1 <= N && ld2 >= p, "rb_boot_f64: bad row split");
     const int ntile = (int)cdiv(p, RB_VT);
     const size_t need = (size_t)ntile * nbt * ((size_t)N * K + K) * sizeof(double);
     if (workspace_bytes < need) {
@@ -551,7 +557,7 @@ extern "C" int plsb200_rb_boot_f64(const double* Xc, int N, int64_t p, const dou
         size_t smem = ((size_t)N * KCV + N + (size_t)KCV * RB_VT + (size_t)N * (RB_VCH + 1)) * sizeof(double);      \
         if (smem > 220 * 1024) { set_err("rb_boot_f64: N=%d too large for shared memory", N); return PLSB200_EUNSUPPORTED; } \
         PLSB_CUDA(cudaFuncSetAttribute(rb_boot_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        rb_boot_kernel<KCV><<<ntile, RB_VT, smem, st>>>(Xc, N, p, Q, W, K, k0, kc, b0, nbt, cell_start, ncell,          \
+        rb_boot_kernel<KCV><<<ntile, RB_VT, smem, st>>>(Xc, N, p, Xc2, n1, ld2, Q, W, K, k0, kc, b0, nbt, cell_start, ncell,          \
                                                         unit_cells, pivot, K,                                       \
                                                         sum, sumsq, Tpart, Npart);                                  \
     } while (0)

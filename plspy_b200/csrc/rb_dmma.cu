@@ -90,6 +90,9 @@ __global__ void rd_pack_kernel(const double* __restrict__ Q, const double* __res
 }
 
 struct RdArgs {
+    const double* Xc2;     // rows [n1, N) of the data matrix live here (row stride ld2); n1 == N: a single matrix
+    long long ld2;
+    int n1;
     const double* Xc;
     const double* pack;
     const double* pivot;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
 #pragma unroll
     for (int s = 0; s < NKS; ++s) {
         const int row = __ldg(a.krow + 4 * s + q);
-        x[s] = (row >= 0 && ok) ? __ldg(a.Xc + (long long)row * a.p + v) : 0.0;
+        x[s] = (row >= 0 && ok) ? __ldg((row < a.n1 ? a.Xc + (long long)row * a.p
+                                                     : a.Xc2 + (long long)(row - a.n1) * a.ld2) + v) : 0.0;
     }
     // running moments live in shared memory (one slot per thread and fragment element): registers are for X
     double* my1 = acc + tid;
@@ -339,6 +343,7 @@ constexpr int GN_T = 64, GN_KC = 32, GN_STR = GN_KC + 4, GN_STAGES = 3, GN_THREA
 
 template <int VEC>   // doubles per cp.async (2 when every row start is 16-byte aligned, else 1)
 __global__ void __launch_bounds__(GN_THREADS) gemm_nt_partial_kernel(const double* __restrict__ A, int NA, long long lda,
+                                                                    const double* __restrict__ A2, int na1, long long lda2,
                                                                     const double* __restrict__ B, int NB, long long ldb,
                                                                     long long p, long long chunk, int ntb,
                                                                     double* __restrict__ part) {
@@ -361,7 +366,8 @@ __global__ void __launch_bounds__(GN_THREADS) gemm_nt_partial_kernel(const doubl
             {
                 const int row = ti * GN_T + r;
                 const int nb = row < NA ? (int)left * 8 : 0;
-                cp_async_zfill<VEC * 8>(As + (st * GN_T + r) * GN_STR + cc, nb ? A + (long long)row * lda + vv : A, nb);
+                const double* rp = row < na1 ? A + (long long)row * lda : A2 + (long long)(row - na1) * lda2;
+                cp_async_zfill<VEC * 8>(As + (st * GN_T + r) * GN_STR + cc, nb ? rp + vv : A, nb);
             }
             {
                 const int row = tj * GN_T + r;
@@ -506,12 +512,14 @@ extern "C" size_t plsb200_rb_boot_dmma_f64_workspace(int N, int64_t p, int K, in
     return rd_layout(r, N, p, nbt, want_t != 0).total;
 }
 
-extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Q, const double* W, int K,
-                                        int b0, int nbt, const int32_t* cell_start_host, int ncell, int unit_cells,
+extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, const double* Xc2, int n1, int64_t ld2,
+                                        const double* Q, const double* W, int K, int b0, int nbt, const int32_t* cell_start_host, int ncell, int unit_cells,
                                         const double* pivot, double* sum, double* sumsq, double* T, double* nrm2,
                                         void* workspace, size_t workspace_bytes, void* stream) {
     PLSB_CHECK_ARG(Xc && Q && cell_start_host && sum && sumsq && nrm2 && workspace, "rb_boot_dmma_f64: null pointer");
     PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && nbt > 0 && ncell > 0, "rb_boot_dmma_f64: bad shape");
+    if (Xc2 == nullptr) { n1 = N; ld2 = p; }
+    PLSB_CHECK_ARG(n1 > 0 && n1 <= N && ld2 >= p, "rb_boot_dmma_f64: bad row split");
     RdPlan r;
     if (!rd_plan(N, K, cell_start_host, ncell, unit_cells, r)) {
         set_err("rb_boot_dmma_f64: design not supported (N=%d, %d cells): use rb_boot_f64", N, ncell);
@@ -537,7 +545,7 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
     PLSB_LAUNCH_CHECK("rd_pack_kernel");
     for (int pass = 0; pass < r.npass; ++pass) {
         RdArgs a;
-        a.Xc = Xc; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
+        a.Xc = Xc; a.Xc2 = Xc2; a.n1 = n1; a.ld2 = ld2; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
         a.VSt = d_vst; a.Npart = d_npart; a.p = p; a.Kfull = K; a.k0 = pass * r.kcp;
         a.kc = K - a.k0 < r.kcp ? K - a.k0 : r.kcp;
         a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell; a.nwarps = L.nwarps;
@@ -556,13 +564,14 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
             const size_t smem = (size_t)2 * GN_STAGES * GN_T * GN_STR * sizeof(double);
             dim3 grid((unsigned)(L.nta * L.ntb), (unsigned)L.nsplit);
             const bool vec2 = (p % 2 == 0) && ((reinterpret_cast<uintptr_t>(Xc) & 15) == 0) &&
-                              ((reinterpret_cast<uintptr_t>(d_vst) & 15) == 0);
+                              ((reinterpret_cast<uintptr_t>(d_vst) & 15) == 0) &&
+                              (n1 == N || (((reinterpret_cast<uintptr_t>(Xc2) & 15) == 0) && ld2 % 2 == 0));
             if (vec2) {
                 PLSB_CUDA(cudaFuncSetAttribute(gemm_nt_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                gemm_nt_partial_kernel<2><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
+                gemm_nt_partial_kernel<2><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, Xc2, n1, ld2, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
             } else {
                 PLSB_CUDA(cudaFuncSetAttribute(gemm_nt_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                gemm_nt_partial_kernel<1><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
+                gemm_nt_partial_kernel<1><<<grid, GN_THREADS, smem, st>>>(Xc, N, p, Xc2, n1, ld2, d_vst, nbt * r.kcp, p, p, L.chunk, L.ntb, d_gpart);
             }
             PLSB_LAUNCH_CHECK("gemm_nt_partial_kernel");
             const long long n = (long long)nbt * N * a.kc;

@@ -60,7 +60,7 @@ def _svd_through_gram(eng, W, Gw, coef, project=None):
     """U (K x K), s (K,), V (p x K, device) of M = coef^T W given Gw = W W^T; `project(c)` = W^T c when W is not
     held as one matrix."""
     C = eng.to_device(coef, torch.float64)
-    B = C.T @ Gw @ C
+    B = eng.quad_form(Gw, C)
     B = 0.5 * (B + B.T)
     ev, U = _eigh_desc(eng, B)
     U = _fix_signs(U)
@@ -97,7 +97,7 @@ def contrast_task(eng, cond_order, contrasts):
     K = Abar.shape[0]
     R, V = both[:, :K].T.contiguous(), both[:, K:].contiguous()
     Ed = eng.to_device(E, torch.float64)
-    VtV = eng.to_host(Ed.T @ eng.G @ Ed)                                    # V^T V in N-space
+    VtV = eng.to_host(eng.quad_form(eng.G, Ed))                                  # V^T V in N-space
     VtV = 0.5 * (VtV + VtV.T)
     s = np.sqrt(np.maximum(np.diagonal(VtV), 0.0))
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -138,7 +138,7 @@ def contrast_behaviour(eng, Y, cond_order, contrasts):
     K = Cy.shape[1]
     R, V = both[:, :K].T.contiguous(), both[:, K:].contiguous()
     Ed = eng.to_device(E, torch.float64)
-    VtV = eng.to_host(Ed.T @ Gz @ Ed)
+    VtV = eng.to_host(eng.quad_form(Gz, Ed))
     VtV = 0.5 * (VtV + VtV.T)
     s = np.sqrt(np.maximum(np.diagonal(VtV), 0.0))
     XL = eng.xv(V)
@@ -160,7 +160,7 @@ def multiblock(eng, pls_alg, cond_order, mctype, bscan, Ybscan, contrasts=None):
     C1[:N, tcol] = Lop.T
     C1[N:, bcol] = cf._behaviour_coefficients(Ybscan, co[:, list(bscan)])
     C1d = eng.to_device(C1, torch.float64)
-    d2row = eng.to_host(((Gw @ C1d) * C1d).sum(dim=0))
+    d2row = eng.to_host(eng.nspace_coef(Gw, C1d[None])[0][0])                  # diag(C1^T Gw C1)
     with np.errstate(divide="ignore", invalid="ignore"):
         rn = np.where(d2row > 0, 1.0 / np.sqrt(np.where(d2row > 0, d2row, 1.0)), 0.0)
     Cn = C1 * rn[None, :]                                          # normalised rows (norm_opt, :503-505)
@@ -178,7 +178,7 @@ def multiblock(eng, pls_alg, cond_order, mctype, bscan, Ybscan, contrasts=None):
         both = project(np.concatenate([Cn, E], axis=1))
         M, V = both[:, :K].T.contiguous(), both[:, K:].contiguous()
         Ed = eng.to_device(E, torch.float64)
-        VtV = eng.to_host(Ed.T @ Gw @ Ed)
+        VtV = eng.to_host(eng.quad_form(Gw, Ed))
         s = np.sqrt(np.maximum(np.diagonal(0.5 * (VtV + VtV.T)), 0.0))
     XV = eng.xv(V)                                                 # X @ V (un-normalised V)
     st.pop("Zb", None)

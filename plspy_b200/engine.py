@@ -223,6 +223,17 @@ class Engine:
                   "gram_f64")
         return G
 
+    def gram_stacked(self, M1, M2):
+        """Gram matrix of the row stack [M1; M2] ((n1 + n2) x p) without building it (multiblock: [X; Zb])."""
+        n1, n2, p = int(M1.shape[0]), int(M2.shape[0]), int(M1.shape[1])
+        assert int(M2.shape[1]) == p
+        with torch.cuda.device(self.device):
+            ws = self._ws(lib.plsb200_gram_f64_workspace(n1 + n2, p))
+            G = self._empty(n1 + n2, n1 + n2)
+            check(lib.plsb200_gram_stacked_f64(self._p(M1), n1, int(M1.stride(0)), self._p(M2), n2, int(M2.stride(0)), p,
+                                               self._p(G), self._p(ws), ws.numel(), self._stream()), "gram_stacked_f64")
+        return G
+
     @property
     def G(self):
         """G = X X^T (N x N), computed once per engine."""
@@ -304,6 +315,22 @@ class Engine:
             check(lib.plsb200_nspace_gram_f64(self._p(G), self.N, self._p(E), K, self._p(idx), R, self._p(d2),
                                               self._p(B), self._stream()), "nspace_gram_f64")
         return B
+
+    def quad_form(self, G, C):
+        """C^T G C (K x K) for a device Gram matrix G (N x N) and coefficients C (N x K): the K x K products of the
+        device-side original analysis, on the N-space kernel (no library GEMM)."""
+        C = self.to_device(C, F64).contiguous()
+        N, K = int(C.shape[0]), int(C.shape[1])
+        if (2 * N * K + K) * 8 + N * 4 <= 200 * 1024:         # one column chunk: the kernel writes the full K x K block
+            ident = torch.arange(N, dtype=I32, device=self.device)[None].contiguous()
+            d2 = self._empty(1, K); B = self._empty(1, K, K)
+            with torch.cuda.device(self.device):
+                check(lib.plsb200_nspace_gram_f64(self._p(G), N, self._p(C), K, self._p(ident), 1, self._p(d2),
+                                                  self._p(B), self._stream()), "nspace_gram_f64")
+            return B[0]
+        # column chunks: T = C^T (G C) diag(1 / sqrt(d2)) from the kernel, un-normalised again (d2 = 0 <=> zero column)
+        d2, T = self.nspace_coef(G, C[None], Lmat=C.T.contiguous())
+        return T[0] * torch.sqrt(torch.clamp(d2[0], min=0.0))[None, :]
 
     def perm_count(self, d2, s_ref, totcov_ref, thresh, counts=None, mb_total=None):
         d2 = self.to_device(d2, F64)
@@ -549,14 +576,19 @@ class Engine:
                                           self._stream()), "rb_coef_f64")
         return Q, W, Yz
 
-    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, unit_cells=0, max_ws_bytes=2 << 30, want_t=True):
+    def rb_boot(self, Xc, Q, W, cell_start, pivot=None, unit_cells=0, max_ws_bytes=2 << 30, want_t=True, X2=None):
         """p-space pass over all bootstraps in Q: returns (sum, sumsq) of VS - pivot (p x K),
         T (R x N x K) = Xc @ VS_b (None when want_t is False) and nrm2 (R x K).
         Runs on the FP64 tensor path (plsb200_rb_boot_dmma_f64) when the design fits its register-resident
-        fragments, else on the general FMA kernel."""
+        fragments, else on the general FMA kernel.  `X2`: the data matrix is the row stack [Xc; X2] (not built: the
+        kernels take the two row segments; multiblock bootstraps pass [Xcb; X])."""
         cs_host = np.ascontiguousarray(np.asarray(cell_start, dtype=np.int32))
         R, N, K = int(Q.shape[0]), int(Q.shape[1]), int(Q.shape[2])
         p = int(Xc.shape[1])
+        n1 = int(Xc.shape[0])
+        ld2 = int(X2.stride(0)) if X2 is not None else p
+        if n1 + (int(X2.shape[0]) if X2 is not None else 0) != N:
+            raise ValueError("rb_boot: coefficient rows do not match the data matrix")
         ncell = int(cs_host.size) - 1
         s1 = torch.zeros(p, K, dtype=F64, device=self.device); s2 = torch.zeros_like(s1)
         T = self._empty(R, N, K) if want_t else None
@@ -575,7 +607,7 @@ class Engine:
                 self._mark("rb_boot")
                 for b0 in range(0, R, nbt):
                     n = min(nbt, R - b0)
-                    check(lib.plsb200_rb_boot_dmma_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n,
+                    check(lib.plsb200_rb_boot_dmma_f64(self._p(Xc), N, p, self._p(X2), n1, ld2, self._p(Q), self._p(W), K, b0, n,
                                                        cs_host.ctypes.data, ncell, int(unit_cells), self._p(pivot),
                                                        self._p(s1), self._p(s2), self._p(T), self._p(nrm2),
                                                        self._p(ws), ws.numel(), self._stream()), "rb_boot_dmma_f64")
@@ -591,7 +623,7 @@ class Engine:
             self._mark("rb_boot")
             for b0 in range(0, R, nbt):
                 n = min(nbt, R - b0)
-                check(lib.plsb200_rb_boot_f64(self._p(Xc), N, p, self._p(Q), self._p(W), K, b0, n, self._p(cs),
+                check(lib.plsb200_rb_boot_f64(self._p(Xc), N, p, self._p(X2), n1, ld2, self._p(Q), self._p(W), K, b0, n, self._p(cs),
                                               ncell, int(unit_cells), self._p(pivot), self._p(s1),
                                               self._p(s2),
                                               self._p(T), self._p(nrm2), self._p(ws), ws.numel(), self._stream()),

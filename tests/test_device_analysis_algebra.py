@@ -41,6 +41,18 @@ class _NumpyEngine:
     def gram_of(self, M):
         return M @ M.T
 
+    def gram_stacked(self, M1, M2):
+        W = torch.cat([M1, M2], dim=0)
+        return W @ W.T
+
+    def quad_form(self, G, C):
+        C = self.to_device(C, torch.float64)
+        return C.T @ G @ C
+
+    def nspace_coef(self, G, C, Lmat=None):
+        d2 = torch.stack([torch.diagonal(c.T @ G @ c) for c in C])
+        return d2, None
+
     def cell_standardize(self, cells, want_z=True, M=None):
         X = (self.X if M is None else M).numpy()
         Xc, Z = np.zeros_like(X), np.zeros_like(X)
