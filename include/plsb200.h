@@ -181,6 +181,11 @@ int plsb200_cell_standardize_f64(const double* X, int N, int64_t p, int64_t ldx,
                                  int ncell, double* Xc, double* Z, void* stream);
 int plsb200_nspace_coef_f64(const double* G, int N, const double* C, int K, int R, const double* Lmat, int Kt,
                             double* d2, double* T, void* stream);
+/* B[r] = C_r^T G C_r (R x K x K) for explicit coefficients: the Gram matrix of a resampled behaviour / multiblock
+ * cross-block matrix (rows = columns of C_r), input of the per-permutation SVD mode (rotate_method = 0) through
+ * plsb200_sym_eig_f64.  N x K must fit one shared-memory chunk (2 N K doubles <= 200 KB).                       */
+int plsb200_nspace_coef_gram_f64(const double* G, int N, const double* C, int K, int R, double* d2, double* B,
+                                 void* stream);
 int plsb200_rb_coef_f64(const double* Y, int N, int nb, const int32_t* idx, int R, const int32_t* cell_start,
                         int ncell, const double* U, int Kc, int scatter, double* Q, double* W, double* Yz,
                         void* stream);

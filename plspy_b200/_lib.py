@@ -80,6 +80,7 @@ SIGNATURES = {
                                              c_double_p, c_void_p]),
     "plsb200_nspace_coef_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int, c_double_p, c_int, c_double_p,
                                         c_double_p, c_void_p]),
+    "plsb200_nspace_coef_gram_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int, c_double_p, c_double_p, c_void_p]),
     "plsb200_rb_coef_f64": (c_int, [c_double_p, c_int, c_int, c_int32_p, c_int, c_int32_p, c_int, c_double_p, c_int,
                                     c_int, c_double_p, c_double_p, c_double_p, c_void_p]),
     "plsb200_rb_boot_f64_workspace": (c_size_t, [c_int, c_int64, c_int, c_int]),

@@ -195,7 +195,8 @@ def _multiblock_indices(pls_alg, indices, niter, cond_order, bscan, Ybscan, boot
     return indices
 
 
-def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan, Ybscan, indices):
+def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan, Ybscan, indices,
+                     rotate_method=2):
     """bootstrap_permutation.py:305-312, 342-347, 391-393, 413-433 for mb / cmb.  Task rows come from the
     task-permuted X, behaviour rows from the ORIGINAL bscan rows of X with globally permuted Ybscan; every
     row is L2-normalised.  With W = [X; Zb] all of it is N-space: row norms and projected norms are
@@ -228,8 +229,13 @@ def _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast,
     C1[:, N:, torch.as_tensor(bcol, device=eng.device)] = Qb
     d2row, _ = eng.nspace_coef(st["Gw"], C1)                                        # squared row norms
     total = d2row.sum(dim=1)                                                        # ||un-normalised multiblock||_F^2
-    C2 = eng.coef_project(C1, d2row, Ucoef)
-    d2, _ = eng.nspace_coef(st["Gw"], C2)
+    if rotate_method == 0:      # singular values of the permuted (row-normalised) multiblock matrix itself
+        C2 = eng.coef_project(C1, d2row, np.eye(K))
+        d2, _ = eng.sym_eig(eng.nspace_coef_gram(st["Gw"], C2))
+        d2 = torch.clamp(d2, min=0.0)
+    else:
+        C2 = eng.coef_project(C1, d2row, Ucoef)
+        d2, _ = eng.nspace_coef(st["Gw"], C2)
     if pls_alg == "mb":     # s_hat^4 rescale, compared with org_s (:419-427)
         counts, s_hat = eng.perm_count(d2, org_s, totcov_org, 0.0, mb_total=total)
     else:                   # cmb: raw s for the counts, rescaled org_s for the stepdown baseline (:433, :316-319)
@@ -342,8 +348,10 @@ class _ResampleTestPLS(ResampleTest):
         self.CI = CI
         if rotate_method not in (0, 1, 2):
             raise ValueError("rotate_method must be 0 (SVD), 1 (Procrustes) or 2 (derived)")
-        if rotate_method == 0 and self.pls_alg != "mct":
-            raise exceptions.NotImplementedError("rotate_method=0 (per-permutation SVD) is provided for mct only")
+        if rotate_method == 0 and self.pls_alg not in ("mct", "rb", "mb"):
+            raise exceptions.NotImplementedError(
+                "rotate_method=0 (per-permutation SVD) applies to the SVD methods (mct, rb, mb); the contrast methods "
+                "have no SVD (class_functions.py:126-162)")
         self.rotate_method = rotate_method
         _log(f"PLS ALG: {self.pls_alg}")
         eng = engine if engine is not None else (
@@ -411,13 +419,18 @@ class _ResampleTestPLS(ResampleTest):
             of pv ps Q.  U and pv are square orthogonal K x K matrices, so Q = pv^T U exactly and
             s_hat_k^2 = U_k^T (pv ps^2 pv^T) U_k = || permuted^T U_k ||^2: identical to the derived value, and served
             by the same kernels (tests/test_gpu_kernels.py checks this against an explicit numpy Procrustes);
-          0 "SVD": s_hat = the singular values of the permuted cross-block matrix itself (mct only): K x K Gram matrix
-            through G (plsb200_nspace_gram_f64) + one-warp-per-matrix Jacobi eigensolver (plsb200_sym_eig_f64)."""
+          0 "SVD": s_hat = the singular values of the permuted cross-block matrix itself (mct, rb, mb): K x K Gram
+            matrix through G / Gz / Gw (plsb200_nspace_gram_f64, plsb200_nspace_coef_gram_f64) + the Jacobi
+            eigensolver (plsb200_sym_eig_f64).
+        The bootstrap test always aligns a resample with the original latent variables; there Procrustes (1) and
+        derived (2) coincide for the same reason (the rotated salience pv ps Q equals permuted^T U), so
+        `rotate_method` does not change any bootstrap output (tests/test_gpu_kernels.py checks an explicit numpy
+        SVD + Procrustes bootstrap against it)."""
         eng = engine if engine is not None else Engine(X)
         s[np.abs(s) < threshold] = 0
         if pls_alg in ("mb", "cmb"):
             out = _perm_multiblock(eng, X, U, s, cond_order, mctype, niter, pls_alg, contrast, bscan, Xbscan,
-                                   Ybscan, indices)
+                                   Ybscan, indices, rotate_method=rotate_method)
             return (lambda: out) if _defer else out
         org_s = np.copy(s)
         totcov_org = _stepdown_tail(org_s)
@@ -436,8 +449,17 @@ class _ResampleTestPLS(ResampleTest):
                 np.asarray(contrast, dtype=float))
             K = Ucoef.shape[1]
             Gz = _behaviour_state(eng, cells)["Gz"]
-            Q, _, _ = eng.rb_coef(Y, idx_dev, cells, Ucoef, scatter=False)
-            d2, _ = eng.nspace_coef(Gz, Q)
+            if rotate_method == 0:
+                # singular values of the permuted correlation matrix R_r itself: eigenvalues of R_r R_r^T = Q^T Gz Q
+                # with the un-projected row coefficients Q (U = identity)
+                Kr = (len(cells) - 1) * Y.shape[1]
+                Q, _, _ = eng.rb_coef(Y, idx_dev, cells, np.eye(Kr), scatter=False)
+                d2, _ = eng.sym_eig(eng.nspace_coef_gram(Gz, Q))
+                d2 = torch.clamp(d2, min=0.0)
+                K = Kr
+            else:
+                Q, _, _ = eng.rb_coef(Y, idx_dev, cells, Ucoef, scatter=False)
+                d2, _ = eng.nspace_coef(Gz, Q)
             Lop = None
         else:
             Lop, Ucoef, E = _task_operators(pls_alg, cond_order, mctype, U, contrast)

@@ -274,6 +274,14 @@ extern "C" int plsb200_nspace_coef_f64(const double* G, int N, const double* C, 
     return nspace_dispatch(G, N, C, (long long)N * K, K, nullptr, R, Lmat, Kt, d2, T, (cudaStream_t)stream);
 }
 
+extern "C" int plsb200_nspace_coef_gram_f64(const double* G, int N, const double* C, int K, int R, double* d2, double* B,
+                                            void* stream) {
+    PLSB_CHECK_ARG(G && C && d2 && B, "nspace_coef_gram_f64: null pointer");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R >= 0, "nspace_coef_gram_f64: bad shape N=%d K=%d R=%d", N, K, R);
+    if (R == 0) return PLSB200_OK;
+    return nspace_dispatch(G, N, C, (long long)N * K, K, nullptr, R, nullptr, 0, d2, nullptr, (cudaStream_t)stream, B);
+}
+
 extern "C" int plsb200_perm_count_f64(const double* d2, int R, int K, const double* s_ref, const double* totcov_ref,
                                       double thresh, const double* mb_total, int64_t* counts, double* s_hat,
                                       void* stream) {

@@ -288,6 +288,15 @@ class Engine:
                                               self._p(T), self._stream()), "nspace_coef_f64")
         return d2, T
 
+    def nspace_coef_gram(self, G, C):
+        """B[r] = C_r^T G C_r (R x K x K) for explicit per-resample coefficients C (R x N x K)."""
+        R, N, K = int(C.shape[0]), int(C.shape[1]), int(C.shape[2])
+        d2 = self._empty(R, K); B = self._empty(R, K, K)
+        with torch.cuda.device(self.device):
+            check(lib.plsb200_nspace_coef_gram_f64(self._p(G), N, self._p(C), K, R, self._p(d2), self._p(B),
+                                                   self._stream()), "nspace_coef_gram_f64")
+        return B
+
     def nspace(self, E, idx, Lmat=None):
         """d2[r,k] = ||X^T C_r[:,k]||^2 and (optionally) T[r] = Lmat G C_r diag(1/sqrt(d2))."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)

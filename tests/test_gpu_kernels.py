@@ -347,6 +347,78 @@ def test_rotate_methods_svd_and_procrustes_against_numpy(torch_cuda):
                        contrasts=np.linalg.qr(rs.standard_normal((6, 2)))[0], rotate_method=0)
 
 
+def test_rotate_method_svd_for_behaviour_and_multiblock_against_numpy(torch_cuda):
+    """rotate_method=0 for rb and mb: the permuted cross-block matrix is rebuilt explicitly with the oracle's builders
+    and decomposed with np.linalg.svd (no reference code exists for this mode: "no reference oracle")."""
+    import oracle
+    import plspy_b200
+    rs = np.random.RandomState(12)
+    groups, C, p, nb, P = (7, 8), 3, 300, 2, 25
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)); X[:7, :40] += 1.0
+    Y = rs.standard_normal((N, nb)) + 0.4 * X[:, :nb]
+    co = np.array([[n] * C for n in groups])
+    # rb
+    np.random.seed(5)
+    res = plspy_b200.PLS(X.copy(), groups, C, Y=Y.copy(), num_perm=P, num_boot=0, pls_method="rb", rotate_method=0)
+    rt = res.resample_tests
+    idx = rt.perm_debug_dict["indices"]
+    sv = np.array([np.linalg.svd(oracle.compute_corr(X, Y[idx[r]], co), compute_uv=False) for r in range(P)])
+    np.testing.assert_allclose(rt.perm_debug_dict["s_list"], sv, rtol=1e-9, atol=1e-11)
+    np.testing.assert_array_equal(rt.permute_ratio, (sv >= res.s).sum(0) / (P + 1))
+    # mb (bscan = [0, 2]): singular values of the row-normalised permuted multiblock matrix, then the s^4 rescale
+    bscan = [0, 2]
+    np.random.seed(6)
+    res = plspy_b200.PLS(X.copy(), groups, C, Y=Y.copy(), num_perm=P, num_boot=0, pls_method="mb", bscan=bscan,
+                         mctype=0, rotate_method=0)
+    rt = res.resample_tests
+    it, ib = rt.perm_debug_dict["indices"], rt.perm_debug_dict["indices_behaviour"]
+    mask = oracle.bscan_mask(co, bscan)
+    Xb, Yb = X[mask], Y[mask]
+    want = np.empty((P, len(res.s)))
+    for r in range(P):
+        M = oracle.create_multiblock(X[it[r]], co, "mb", bscan, 0, Xbscan=Xb, Ybscan=Yb[ib[r]])
+        raw = oracle.create_multiblock(X[it[r]], co, "mb", bscan, 0, norm_opt=False, Xbscan=Xb, Ybscan=Yb[ib[r]])
+        q = np.linalg.svd(M, compute_uv=False) ** 4
+        want[r] = np.sqrt(q / q.sum() * np.sum(raw ** 2))
+    np.testing.assert_allclose(rt.perm_debug_dict["s_list"], want, rtol=1e-8, atol=1e-10)
+    with pytest.raises(Exception):      # contrast methods have no SVD
+        plspy_b200.PLS(X.copy(), groups, C, Y=Y.copy(), num_perm=3, num_boot=0, pls_method="csb",
+                       contrasts=np.linalg.qr(rs.standard_normal((len(groups) * C * nb, 2)))[0], rotate_method=0)
+
+
+def test_bootstrap_svd_plus_procrustes_equals_the_derived_projection(torch_cuda):
+    """north star: "re-run the SVD plus Procrustes rotation once per resample".  For every bootstrap the cross-block
+    matrix is decomposed with np.linalg.svd and its brain saliences are rotated onto the original latent variables
+    with the Procrustes rotation of the MATLAB PLS toolbox (Q = v u^T from svd(U^T pu)); the standard errors of those
+    rotated saliences are what the GPU path's projection onto the original U yields -- with rotate_method=1 and 2."""
+    import plspy_b200
+    from plspy_b200 import class_functions as cf
+    rs = np.random.RandomState(9)
+    groups, C, p, B = (6, 7), 3, 500, 40
+    N = sum(groups) * C
+    X = rs.standard_normal((N, p)); X[:6, :50] += 1.0
+    co = np.array([[n] * C for n in groups])
+    A = cf._centring_operator(co, 0)
+    U, s, V = cf._run_pls(A @ X)
+    live = s > 1e-8 * s.max()
+    out = {}
+    for rm in (1, 2):
+        np.random.seed(31)
+        out[rm] = plspy_b200.PLS(X.copy(), groups, C, num_perm=0, num_boot=B, mctype=0, pls_method="mct", rotate_method=rm)
+    idx = out[1].resample_tests.boot_debug_dict["indices"]
+    rot = np.empty((B, p, len(s)))
+    for b in range(B):
+        pu, ps, pvt = np.linalg.svd(A @ X[idx[b]], full_matrices=False)       # pu: design side (K x K), pvt: brain side
+        u_, _, vt_ = np.linalg.svd(U.T @ pu)
+        Q = (u_ @ vt_).T                                                      # rotation aligning pu with the original U
+        rot[b] = (pvt.T * ps) @ Q
+    want = rot.std(axis=0)
+    for rm in (1, 2):
+        np.testing.assert_allclose(out[rm].resample_tests.std_errs[:, live], want[:, live], rtol=1e-8)
+    np.testing.assert_array_equal(out[1].resample_tests.boot_ratios, out[2].resample_tests.boot_ratios)
+
+
 def test_rb_boot_dmma_chunked_launches_accumulate(torch_cuda):
     """several launches over bootstrap chunks (small workspace) accumulate the same moments as one launch, and a
     design with more than 16 blocks falls back to the general kernel"""
