@@ -418,6 +418,104 @@ def phase_timeline(run, torch):
                     "to_host_async gpu_ms covers only the enqueue of the copies"}
 
 
+def side_configs(torch, time_budget_s=90.0):
+    """The other BASELINE.json configs that fit one GPU, each through the public `plspy_b200.PLS(...)` call at its full
+    shape and iteration counts (wall seconds of the whole call: index drawing, original analysis, upload, resampling,
+    results on the host; best of 2 after a warm-up), and each checked against the oracle port on a SUBSAMPLE of the
+    iterations at the same shape (the same seed on both sides, so index generation is part of the check).
+    SURVEY.md section 8 table of configs; synthetic data as section 8(d)."""
+    import oracle
+    import plspy_b200
+
+    def data(seed, groups, C, p, nb=0):
+        rs = np.random.RandomState(seed)
+        N = sum(groups) * C
+        X = rs.standard_normal((N, p))
+        ne, row = p // 20, 0
+        for g in groups:
+            for _ in range(C):
+                X[row:row + g, :ne] += 0.5 * rs.standard_normal(ne)
+                row += g
+        Y = (rs.standard_normal((N, nb)) + 0.3 * X[:, :nb]) if nb else None
+        return rs, X, Y
+
+    def rel(a, b, live):
+        a, b = np.asarray(a)[..., live], np.asarray(b)[..., live]
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-9)))
+
+    specs = [
+        ("cfg1", "mct", (10, 10), 3, 10_000, 0, 500, 500, 0, {}, (500, 500, 0)),
+        ("cfg2", "rb", (20, 20), 3, 50_000, 4, 1000, 1000, 0, {}, (8, 8, 0)),
+        ("cfg3", "cst", (25, 25, 25), 4, 200_000, 0, 5000, 5000, 0, {"L": 3}, (8, 8, 0)),
+        ("cfg4", "mb", (30, 30), 4, 200_000, 4, 2000, 2000, 500, {"bscan": [1, 2]}, (2, 2, 1)),
+    ]
+    out = {}
+    t_start = time.perf_counter()
+    for name, method, groups, C, p, nb, P, B, S, extra, sub in specs:
+        if time.perf_counter() - t_start > time_budget_s:
+            out[name] = {"skipped": "time budget of the side records used up"}
+            continue
+        rs, X, Y = data(20260000 + int(name[3:]), groups, C, p, nb)
+        kw = dict(pls_method=method)
+        okw = dict(mctype=0)
+        if method in ("mct", "cst", "mb"):
+            kw["mctype"] = 0
+        if Y is not None:
+            kw["Y"] = Y; okw["Y"] = Y
+        if "L" in extra:
+            contrasts = np.linalg.qr(rs.standard_normal((len(groups) * C, extra["L"])))[0]
+            kw["contrasts"] = contrasts; okw["contrasts"] = contrasts
+        if "bscan" in extra:
+            kw["bscan"] = list(extra["bscan"]); okw["bscan"] = list(extra["bscan"])
+        skw = dict(num_split=S, lv=1) if S else {}
+        ts = []
+        for rep in range(3):
+            np.random.seed(1234 + rep)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            plspy_b200.PLS(X, groups, C, num_perm=P, num_boot=B, **kw, **skw)
+            torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+        units = P + B + 4 * S
+        rec = {"workload": f"{method} PLS, {len(groups)} x {groups[0]} subj x {C} cond x {p} voxels"
+                           + (f", {nb} behaviours" if nb else "") + (f", bscan={extra['bscan']}" if "bscan" in extra else "")
+                           + (f", {extra['L']} contrasts" if "L" in extra else "")
+                           + f", {P} perm + {B} boot" + (f" + {S} splits" if S else ""),
+               "pls_call_s": min(ts[1:]), "resamples_per_s": units / min(ts[1:]),
+               "units": f"{P} + {B}" + (f" + 4 x {S} half-analyses" if S else "")}
+        # ---- oracle check on a subsample at the full shape
+        sp, sb, ss = sub
+        t0 = time.perf_counter()
+        np.random.seed(4321)
+        o = oracle.run_full(method, X, groups, C, nperm=sp, nboot=sb, nsplit=ss, lv=1,
+                            **{k: (v.copy() if hasattr(v, "copy") else v) for k, v in okw.items()})
+        t_or = time.perf_counter() - t0
+        np.random.seed(4321)
+        res = plspy_b200.PLS(X, groups, C, num_perm=sp, num_boot=sb, **kw, **(dict(num_split=ss, lv=1) if ss else {}))
+        rt = res.resample_tests
+        s_o = np.asarray(o["s"])
+        live = np.abs(s_o) > 1e-8 * np.abs(s_o).max()
+        chk = {"against": f"oracle port, {sp} perm + {sb} boot" + (f" + {ss} split" if ss else "") + " at the full shape",
+               "oracle_seconds": t_or,
+               "p_values_equal": bool(np.array_equal(np.asarray(rt.permute_ratio)[live], np.asarray(o["perm"]["permute_ratio"])[live])),
+               "perm_s_hat_max_rel": rel(rt.perm_debug_dict["s_list"], o["perm"]["s_hat"], live),
+               "std_errs_max_rel": rel(rt.std_errs, o["boot"]["std_errs"], live),
+               "boot_ratios_max_rel": rel(rt.boot_ratios, o["boot"]["boot_ratios"], live)}
+        tol = 1e-8 if method in ("mct", "cst") else 1e-6
+        ok = chk["p_values_equal"] and chk["perm_s_hat_max_rel"] < 1e-9 and chk["std_errs_max_rel"] < tol
+        if "LVcorr" in o["boot"]:
+            chk["lvcorr_max_abs"] = float(np.max(np.abs(np.asarray(rt.LVcorr)[..., live] - o["boot"]["LVcorr"][..., live])))
+            ok = ok and chk["lvcorr_max_abs"] < 1e-7
+        if ss:
+            d = np.arange(max(1, int(live.sum()) - 1))
+            a, b_ = res.pls_repro_tt["pls_s_test"], o["tt"]["pls_s_test"]
+            chk["split_s_test_diag_max_rel"] = float(np.max(np.abs(a[d, d, :] - b_[d, d, :]) / np.maximum(np.abs(b_[d, d, :]), 1e-9)))
+            ok = ok and chk["split_s_test_diag_max_rel"] < 1e-6
+        chk["ok"] = bool(ok)
+        rec["check"] = chk
+        out[name] = rec
+        del X, Y, res, o
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -691,6 +789,10 @@ def run_gpu(args):
                 pls_call[f"analysis_{analysis}_{m}"] = min(ts[1:])
                 pls_call[f"analysis_{analysis}_{m}_resamples_per_s"] = (nperm + nboot) / min(ts[1:])
 
+    configs = None
+    if world == 1 and not args.no_side_configs:
+        configs = side_configs(torch)
+
     # ---- CPU baseline: bounded sample of the same workload on the host cores (N=1 only), and -- on exactly the
     # resamples that sample drew -- the parity check of the GPU path against it at the benchmark shape
     cpu = None
@@ -713,7 +815,10 @@ def run_gpu(args):
                    "l2": "inputs larger than L2 (X 480 MB + packed coefficients 146 MB), no explicit flush",
                    "precision_mode": "fp64 exact" if args.precision == "fp64" else "tf32x3 fast mode"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+                "d2h_bytes_per_step": int(d2h),
+                "d2h_note": None if world == 1 else
+                "rank 0 reads the complete results back; the other ranks hold the same (all-reduced) p x K results "
+                "on their devices and fetch them on first access"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -721,6 +826,7 @@ def run_gpu(args):
         "fast_mode": fast_mode,
         "strong": strong,
         "pls_call": pls_call,
+        "configs": configs,
         "step_ms": step_log,
         "check": check,
     }
@@ -771,6 +877,8 @@ def main():
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra fast-mode measurement")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling side record")
     ap.add_argument("--no-pls-call", action="store_true", help="skip the whole-PLS(...)-call timing")
+    ap.add_argument("--no-side-configs", action="store_true",
+                    help="skip the side records of BASELINE configs 1-4 (whole-call timing + oracle check)")
     args = ap.parse_args()
     with _QuietStdout() as quiet:
         args._quiet = quiet
