@@ -54,6 +54,10 @@ int64_t plsb200_launch_count(void);
 int plsb200_copy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
                        size_t height, void* stream);
 
+/* float32 -> float64 widening on the device: X may be stored and uploaded as float32 (plspy_b200/io.py: the data a NIfTI
+ * file holds are float32 / int16; plspy/io/io.py:10-700 assembles them into a float64 matrix on the host)         */
+int plsb200_widen_f32_f64(const float* src, double* dst, int64_t n, void* stream);
+
 /* ---- K1: Gram matrix G = X . X^T (N x N), FP64 DMMA, split over voxel chunks, deterministic --------
  * Replaces the N x p work that every resample redoes in the reference (row gather + means + projection,
  * resample.py:79,153 + class_functions.py:7-95 + bootstrap_permutation.py:404): once G is known every

@@ -21,7 +21,7 @@ def __getattr__(name):
     if name in ("install", "uninstall"):
         from . import plugin
         return getattr(plugin, name)
-    if name in ("plugin", "bootstrap_permutation", "class_functions", "pls", "pls_classes", "resample",
+    if name in ("io", "plugin", "bootstrap_permutation", "class_functions", "pls", "pls_classes", "resample",
                 "split_half_resampling", "engine", "dist", "build", "_lib"):
         import importlib
         return importlib.import_module("." + name, __name__)

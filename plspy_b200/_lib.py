@@ -37,6 +37,7 @@ SIGNATURES = {
     "plsb200_last_error": (ctypes.c_char_p, []),
     "plsb200_launch_count": (c_int64, []),
     "plsb200_copy2d_h2d": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    "plsb200_widen_f32_f64": (c_int, [c_void_p, c_double_p, c_int64, c_void_p]),
     "plsb200_gram_f64_workspace": (c_size_t, [c_int, c_int64]),
     "plsb200_gram_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_gram_stacked_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_int, c_int64, c_int64, c_double_p,

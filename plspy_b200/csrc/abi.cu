@@ -34,3 +34,29 @@ extern "C" int plsb200_copy2d_h2d(void* dst, size_t dst_pitch, const void* src_h
                                 (cudaStream_t)stream));
     return PLSB200_OK;
 }
+
+// float32 -> float64 widening of a device array (X stored as float32 on the host: half the PCIe traffic; the images a
+// NIfTI file holds are float32 / int16, so nothing is lost relative to the float64 array the reference computes on)
+namespace plsb {
+__global__ void widen_f32_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        *reinterpret_cast<double2*>(dst + i) = make_double2((double)v.x, (double)v.y);
+        *reinterpret_cast<double2*>(dst + i + 2) = make_double2((double)v.z, (double)v.w);
+    } else {
+        for (; i < n; ++i) dst[i] = (double)src[i];
+    }
+}
+}  // namespace plsb
+
+extern "C" int plsb200_widen_f32_f64(const float* src, double* dst, int64_t n, void* stream) {
+    PLSB_CHECK_ARG(src && dst && n >= 0, "widen_f32_f64: bad arguments");
+    PLSB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                   "widen_f32_f64: pointers must be 16-byte aligned");
+    if (n == 0) return PLSB200_OK;
+    const long long nthreads = (n + 3) / 4;
+    plsb::widen_f32_f64_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    PLSB_LAUNCH_CHECK("widen_f32_f64_kernel");
+    return PLSB200_OK;
+}

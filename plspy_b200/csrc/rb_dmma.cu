@@ -24,6 +24,7 @@ constexpr int RD_MAXKS = 96;
 
 struct RdPlan {
     int nks, nblk, kcp, npass, nstage, warps;   // warps: template bucket (8 or 16) = upper bound of the launch
+    int ks_unit;                                // first k-step of the trailing unit cells
     size_t stage_doubles;        // packed coefficients + weights of one bootstrap and one pass
     size_t smem_bytes;
     int krow[RD_MAXKS * 4];      // k-step slot -> row of Xc (-1 = padding)
@@ -37,17 +38,20 @@ static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, 
     r.ncell = ncell;
     int s = 0;
     r.cend[0] = r.cend[1] = r.cend[2] = 0;
+    r.ks_unit = -1;
     for (int c = 0; c < ncell; ++c) {
         const int n = cs[c + 1] - cs[c];
         if (n < 1) return false;
         const int ks = (n + 3) / 4;
         if (s + ks > RD_MAXKS) return false;
+        if (c >= ncell - unit_cells && r.ks_unit < 0) r.ks_unit = s;
         for (int t = 0; t < ks * 4; ++t) r.krow[s * 4 + t] = t < n ? cs[c] + t : -1;
         r.celln[c] = c >= ncell - unit_cells ? -(double)n : (double)n;
         r.cend[(s + ks - 1) >> 5] |= 1u << ((s + ks - 1) & 31);
         s += ks;
     }
     r.nks = (s + 3) / 4 * 4;                       // kernels are instantiated for multiples of 4 k-steps
+    if (r.ks_unit < 0) r.ks_unit = r.nks;
     for (int t = s; t < r.nks; ++t)
         for (int q = 0; q < 4; ++q) r.krow[t * 4 + q] = -1;
     r.nblk = K <= 8 ? 1 : (K <= 16 ? 2 : 3);
@@ -104,6 +108,7 @@ struct RdArgs {
     double* Npart;     // [nbt][kcp][tiles*8]
     long long p;
     int Kfull, k0, kc, nbt, npass, pass, nstage, ncell, nwarps;
+    int ks_unit;       // first k-step of the trailing unit cells (plain linear rows: no block moments needed); nks if none
     uint32_t cend[3];
 };
 
@@ -212,9 +217,11 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
         int cell = 0;
 #pragma unroll
         for (int s = 0; s < NKS; ++s) {
-            const double wx = ws[4 * s] * x[s];
-            m1 += wx;
-            m2 = fma(wx, x[s], m2);
+            if (s < a.ks_unit) {                                  // (unit cells are not standardised: no moments)
+                const double wx = ws[4 * s] * x[s];
+                m1 += wx;
+                m2 = fma(wx, x[s], m2);
+            }
             if ((a.cend[s >> 5] >> (s & 31)) & 1u) {              // warp-uniform: last k-step of a cell
                 m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
                 m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
@@ -267,9 +274,11 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                     const double b = bs[(s * NBLK + j) * 32];
                     dmma884(vs[j][0], vs[j][1], xs, b);
                 }
-                const double wx = ws[4 * s] * x[s];
-                m1 += wx;
-                m2 = fma(wx, x[s], m2);
+                if (s < a.ks_unit) {                              // warp-uniform; the task rows of a multiblock pass
+                    const double wx = ws[4 * s] * x[s];           // (two thirds of its k-steps) skip the moment work
+                    m1 += wx;
+                    m2 = fma(wx, x[s], m2);
+                }
                 if ((a.cend[s >> 5] >> (s & 31)) & 1u) {          // warp-uniform: last k-step of a cell
                     m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
                     m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
@@ -548,7 +557,7 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
         a.Xc = Xc; a.Xc2 = Xc2; a.n1 = n1; a.ld2 = ld2; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
         a.VSt = d_vst; a.Npart = d_npart; a.p = p; a.Kfull = K; a.k0 = pass * r.kcp;
         a.kc = K - a.k0 < r.kcp ? K - a.k0 : r.kcp;
-        a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell; a.nwarps = L.nwarps;
+        a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell; a.nwarps = L.nwarps; a.ks_unit = r.ks_unit;
         a.cend[0] = r.cend[0]; a.cend[1] = r.cend[1]; a.cend[2] = r.cend[2];
         int rc;
         switch (r.nblk) {

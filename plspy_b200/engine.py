@@ -122,6 +122,14 @@ class Engine:
         time took 17 ms each, a share plus the all-gather takes 2."""
         from . import dist
         size = dist.world()[1]
+        if torch.is_tensor(X) and X.dtype == torch.float32 and X.dim() == 2:
+            # float32 storage (plspy_b200/io.py): half the bytes over PCIe, widened on the device
+            x32 = X.to(self.device, non_blocking=True).contiguous()
+            out = torch.empty(x32.shape, dtype=F64, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib.plsb200_widen_f32_f64(x32.data_ptr(), out.data_ptr(), x32.numel(), self._stream()),
+                      "widen_f32_f64")
+            return out
         on_host = not (torch.is_tensor(X) and X.is_cuda)
         if (size == 1 and on_host and torch.is_tensor(X) and X.dim() == 2 and X.dtype == F64 and X.is_pinned()
                 and X.is_contiguous() and X.numel() * 8 >= self.PIPELINED_UPLOAD_MIN_BYTES):

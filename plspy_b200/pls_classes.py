@@ -79,6 +79,12 @@ class PLSBase(abc.ABC):
         if len(X.shape) != 2 or (need_y and len(Y.shape) != 2):
             raise exceptions.ImproperShapeError(
                 "Input matrices must be 2-dimensional." if need_y else "Input matrix must be 2-dimensional.")
+        if hasattr(X, "is_pinned") and hasattr(X, "numpy") and not X.is_cuda:
+            # a host tensor from plspy_b200.io.assemble_pinned: the engine uploads the (pinned) tensor itself, the
+            # host-side code works on its numpy view (float32 storage: a widened copy, meant for analysis="device")
+            if self._engine_kwargs.get("engine") is None:
+                self._x_tensor = X
+            X = X.numpy() if X.dtype.is_floating_point and X.element_size() == 8 else X.numpy().astype(np.float64)
         self.X = X
         if need_y:
             self.Y = Y
@@ -133,12 +139,18 @@ class PLSBase(abc.ABC):
             return False
         if self._engine_kwargs.get("engine") is None:
             from .engine import Engine
-            self._engine_kwargs["engine"] = Engine(self.X, device=self._engine_kwargs.get("device"),
+            self._engine_kwargs["engine"] = Engine(getattr(self, "_x_tensor", None) if getattr(self, "_x_tensor", None)
+                                                   is not None else self.X, device=self._engine_kwargs.get("device"),
                                                    precision=self._engine_kwargs.get("precision", "fp64"))
         return True
 
     def _resample(self, Y, mctype, preprocess, **kw):
         V = getattr(self, "_V_dev", None)
+        xt = getattr(self, "_x_tensor", None)
+        if xt is not None and self._engine_kwargs.get("engine") is None and (self.num_perm > 0 or self.num_boot > 0):
+            from .engine import Engine
+            self._engine_kwargs["engine"] = Engine(xt, device=self._engine_kwargs.get("device"),
+                                                   precision=self._engine_kwargs.get("precision", "fp64"))
         self.resample_tests = bootstrap_permutation.ResampleTest._create(
             self.pls_alg, self.X, Y, self.U, self.s, self.V if V is None else V, self.cond_order, mctype, preprocess=preprocess,
             nperm=self.num_perm, nboot=self.num_boot, CI=self.CI,

@@ -134,3 +134,28 @@ def test_too_tall_design_fails_loudly():
     X, _ = _data((220, 220), 3, 64, seed=9)     # N = 1320 > 1280
     with pytest.raises(PlsB200Error):
         plspy_b200.PLS(X, (220, 220), 3, num_perm=0, num_boot=3, pls_method="mct")
+
+
+def test_pinned_tensor_input_and_float32_storage():
+    """X assembled by plspy_b200.io into pinned host memory is uploaded as it is; float32 storage (half the PCIe
+    bytes, widened on the device) gives the results of the float64 analysis of the same numbers"""
+    import plspy_b200
+    from plspy_b200 import io
+    rs = np.random.RandomState(5)
+    sizes, C, p = (6, 5), 3, 700
+    groups = [[[rs.standard_normal(p).astype(np.float32) for _ in range(C)] for _ in range(n)] for n in sizes]
+    X64, gs, nc = io.assemble_pinned(groups, dtype=np.float64)
+    X32, _, _ = io.assemble_pinned(groups, dtype=np.float32)
+    assert X64.is_pinned() and X32.is_pinned()
+    out = []
+    for X in (X64.numpy().copy(), X64, X32):
+        np.random.seed(3)
+        out.append(plspy_b200.PLS(X, gs, nc, num_perm=20, num_boot=20, pls_method="mct", analysis="device"))
+    ref = out[0].resample_tests
+    for r in out[1:]:
+        np.testing.assert_array_equal(r.resample_tests.permute_ratio, ref.permute_ratio)
+        np.testing.assert_allclose(r.resample_tests.std_errs, ref.std_errs, rtol=1e-12)
+        np.testing.assert_allclose(r.s, out[0].s, rtol=1e-12)
+    np.random.seed(3)
+    host = plspy_b200.PLS(X64, gs, nc, num_perm=20, num_boot=20, pls_method="mct")      # host analysis on the numpy view
+    np.testing.assert_array_equal(host.resample_tests.permute_ratio, ref.permute_ratio)

@@ -259,3 +259,19 @@ def test_lazy_debug_dict_behaves_like_the_reference_plain_dict():
     assert dict(d) == {"s_list": 1, "indices": 2, "right_sv_sampled": 3}
     assert sorted(d.values()) == [1, 2, 3] and dict(d.items())["indices"] == 2
     assert sorted(calls) == ["i", "r"]                    # each lazy entry computed exactly once
+
+
+def test_io_assembly_matches_the_reference_row_order():
+    """plspy_b200.io: rows in the order of the reference's concat_assemble_group / concat_flatten_all_groups
+    (plspy/io/io.py:654-699), written once into one host buffer; float32 storage is exact for float32 sources"""
+    from plspy_b200 import io
+    rs = np.random.RandomState(2)
+    sizes, C, shape = (3, 4), 2, (5, 6)
+    groups = [[[rs.standard_normal(shape).astype(np.float32) for _ in range(C)] for _ in range(n)] for n in sizes]
+    want = io.concat_flatten_all_groups([io.concat_assemble_group(g) for g in groups]).astype(np.float64)
+    for dt in (np.float64, np.float32):
+        X, gs, nc = io.assemble_pinned(groups, dtype=dt)
+        assert gs == sizes and nc == C and tuple(X.shape) == (sum(sizes) * C, 30)
+        np.testing.assert_array_equal(X.numpy().astype(np.float64), want)      # exact, also through float32 storage
+    with pytest.raises(ValueError):
+        io.assemble_pinned([[[np.zeros(4)], [np.zeros(5)]]])
