@@ -63,6 +63,15 @@ int boot_rs_moments(const double* X, int N, int64_t p, int64_t ldx, const double
                     const double* pivot, double* sum, double* sumsq, void* workspace, size_t workspace_bytes,
                     cudaStream_t st);
 
+// output-stationary bootstrap-moments path for N > 320 (boot_os.cu); same contract as the row-split path
+bool boot_os_usable(const double* X, int64_t p, int64_t ldx);
+size_t boot_os_coef_bytes(int N, int K, int R);
+size_t boot_os_workspace(int N, int64_t p, int K, int R);
+int boot_os_pack(const double* E, int N, int K, const int32_t* idx, int R, double* coef, cudaStream_t st);
+int boot_os_moments(const double* X, int N, int64_t p, int64_t ldx, const double* coef, int K, int R,
+                    const double* pivot, double* sum, double* sumsq, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st);
+
 // ---------------------------------------------------------------- device side
 #ifdef __CUDACC__
 

@@ -190,9 +190,9 @@ def test_boot_moments_row_split(torch_cuda, N, p, K, R):
 def test_error_reporting(torch_cuda):
     from plspy_b200.engine import Engine
     from plspy_b200._lib import PlsB200Error
-    eng = Engine(np.zeros((1400, 10)))
+    eng = Engine(np.zeros((40, 10)))
     with pytest.raises(PlsB200Error):
-        eng.boot_moments(np.zeros((1400, 3)), np.zeros((2, 1400), np.int32))   # N > 1280 is not supported
+        eng.sym_eig(np.zeros((1, 113, 113)))                                   # K > 112 is not supported
 
 
 @pytest.mark.parametrize("K", [3, 6, 12, 16, 24, 32, 33, 48, 64, 100, 112])
