@@ -149,7 +149,7 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
     __syncthreads();
 
     // warp 0 (also a consumer) is the producer: the A block of a stage is one contiguous 33 KB piece of the image
-    // (three bulk copies), the coefficient block one of 24 KB (two)
+    // (one bulk copy), the coefficient block one of 24 KB (another)
     const double* atile = Ximg + (size_t)(blockIdx.x / nsplit) * spc * OS_A_DOUBLES;
     auto issue = [&](int g, int slot) {
         const int ct = ct0 + g / spc, sk = g % spc;
@@ -159,14 +159,9 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
         const double* asrc = atile + (size_t)sk * OS_A_DOUBLES;
         const double* bsrc = coef + ((size_t)ct * nks + (size_t)sk * OS_KS) * (OS_NB * 32);
         constexpr uint32_t AB = (uint32_t)OS_A_DOUBLES * 8u, BB = (uint32_t)OS_B_DOUBLES * 8u;
-        if (lane == 0) bulk_g2s(A, asrc, 16384u, full + slot);
-        else if (lane == 1) bulk_g2s(A + 2048, asrc + 2048, 16384u, full + slot);
-        else if (lane == 2) bulk_g2s(A + 4096, asrc + 4096, AB - 32768u, full + slot);
-        else if (lane == 3) bulk_g2s(A + OS_A_DOUBLES, bsrc, 16384u, full + slot);
-        else if (lane == 4) bulk_g2s(A + OS_A_DOUBLES + 2048, bsrc + 2048, BB - 16384u, full + slot);
+        if (lane == 0) bulk_g2s(A, asrc, AB, full + slot);
+        else if (lane == 1) bulk_g2s(A + OS_A_DOUBLES, bsrc, BB, full + slot);
     };
-    static_assert(OS_A_DOUBLES * 8 > 32768 && OS_A_DOUBLES * 8 <= 49152 && OS_B_DOUBLES * 8 > 16384 &&
-                  OS_B_DOUBLES * 8 <= 32768, "copy split of a stage");
     if (warp == 0)
         for (int g = 0; g < min(OS_NSTAGE, nit); ++g) issue(g, g);
 
@@ -177,6 +172,10 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
 #pragma unroll
         for (int jm = 0; jm < NACC; ++jm) { s1[mt][jm][0] = s1[mt][jm][1] = 0.0; s2[mt][jm][0] = s2[mt][jm][1] = 0.0; }
 
+    const int nbp = 8 * NACC / Kp;             // resamples per period of 8 NACC columns
+    // the two warps of an SM sub-partition (w and w + 4) run half a stage apart, so that one of them keeps the DMMA
+    // pipe busy while the other folds a finished tile or waits at a stage boundary (as in boot_moments_kernel)
+    if (warp >= 4) __nanosleep((unsigned)(OS_KS * 24 * 8));
     int slot = 0, prev_slot = 0, g = 0;
     uint32_t phase = 0, prev_phase = 0;
     for (int ct = ct0; ct < ct1; ++ct) {
@@ -216,19 +215,23 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
             if (++slot == OS_NSTAGE) { slot = 0; phase ^= 1u; }
         }
         // fold the finished tile: (VS - pivot) into the running moments; padding columns (k >= K) and resamples
-        // beyond R are masked
-        const long long col0 = (long long)ct * OS_TN + wn * 48;
+        // beyond R are masked.  32-bit index arithmetic only: the column of an accumulator within its period,
+        // c = 8 (j mod NACC) + 2q + e, fixes k and the resample slot for the whole kernel.
+        const int rbase = ct * (OS_TN / Kp) + wn * (48 / Kp);          // first resample of this warp's 48 columns
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             const long long v = v0 + wm * 32 + mt * 8 + vr;
+            const bool vok = v < p;
+            const double* pv = pivot != nullptr ? pivot + (vok ? v : 0) * K : nullptr;
 #pragma unroll
             for (int j = 0; j < 6; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const long long col = col0 + 8 * j + 2 * q + e;
-                    const int k = (int)(col % Kp);
-                    if (k < K && col / Kp < R && v < p) {
-                        const double dd = acc[mt][j][e] - (pivot != nullptr ? __ldg(pivot + v * K + k) : 0.0);
+                    const int c = 8 * (j % NACC) + 2 * q + e;
+                    const int rr = c / Kp, k = c - rr * Kp;
+                    const int r = rbase + (j / NACC) * nbp + rr;
+                    if (k < K && r < R && vok) {
+                        const double dd = acc[mt][j][e] - (pv != nullptr ? __ldg(pv + k) : 0.0);
                         s1[mt][j % NACC][e] += dd;
                         s2[mt][j % NACC][e] = fma(dd, dd, s2[mt][j % NACC][e]);
                     }
@@ -243,7 +246,6 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
     double* r2 = ring + OS_TM * Kp;
     for (int i = tid; i < 2 * OS_TM * Kp; i += 256) ring[i] = 0.0;
     __syncthreads();
-    const int nbp = 8 * NACC / Kp;             // resamples per period
     for (int half = 0; half < 2; ++half) {
         if (wn == half) {
             for (int round = 0; round < nbp; ++round) {
