@@ -433,9 +433,16 @@ static bool tall_os() {
     static const char* const env = getenv("PLSB200_TALL");
     return !(env && env[0] == 'r');
 }
+// N <= 320: the register-resident kernel of this file unless PLSB200_EXACT=os routes every design through boot_os.cu
+static bool short_os() {
+    static const char* const env = getenv("PLSB200_EXACT");
+    return env && env[0] == 'o';
+}
+static bool use_other(int N) { return N > 320 || short_os(); }
+static bool use_os(int N) { return N > 320 ? tall_os() : true; }
 
 extern "C" size_t plsb200_boot_coef_bytes(int N, int K, int R) {
-    if (N > 320) return tall_os() ? boot_os_coef_bytes(N, K, R) : boot_rs_coef_bytes(N, K, R);
+    if (use_other(N)) return use_os(N) ? boot_os_coef_bytes(N, K, R) : boot_rs_coef_bytes(N, K, R);
     BootPlan b;
     if (!boot_plan(N, K, R, 1, b)) return 0;
     return (size_t)b.nper * b.stage_doubles * sizeof(double);
@@ -444,8 +451,8 @@ extern "C" size_t plsb200_boot_coef_bytes(int N, int K, int R) {
 extern "C" int plsb200_boot_coef_pack_f64(const double* E, int N, int K, const int32_t* idx, int R, double* coef,
                                           void* stream) {
     PLSB_CHECK_ARG(E && idx && coef, "boot_coef_pack_f64: null pointer");
-    if (N > 320)
-        return tall_os() ? boot_os_pack(E, N, K, idx, R, coef, (cudaStream_t)stream)
+    if (use_other(N))
+        return use_os(N) ? boot_os_pack(E, N, K, idx, R, coef, (cudaStream_t)stream)
                          : boot_rs_pack(E, N, K, idx, R, coef, (cudaStream_t)stream);
     BootPlan b;
     if (!boot_plan(N, K, R, 1, b)) {
@@ -462,7 +469,7 @@ extern "C" int plsb200_boot_coef_pack_f64(const double* E, int N, int K, const i
 }
 
 extern "C" size_t plsb200_boot_moments_f64_workspace(int N, int64_t p, int K, int R) {
-    if (N > 320) return tall_os() ? boot_os_workspace(N, p, K, R) : boot_rs_workspace(N, p, K, R);
+    if (use_other(N)) return use_os(N) ? boot_os_workspace(N, p, K, R) : boot_rs_workspace(N, p, K, R);
     BootPlan b;
     if (!boot_plan(N, K, R, p, b)) return 0;
     return b.nsplit > 1 ? (size_t)2 * b.nsplit * p * K * sizeof(double) : 16;
@@ -473,8 +480,8 @@ extern "C" int plsb200_boot_moments_f64(const double* X, int N, int64_t p, int64
                                         size_t workspace_bytes, void* stream) {
     PLSB_CHECK_ARG(X && coef && sum && sumsq, "boot_moments_f64: null pointer");
     PLSB_CHECK_ARG(p > 0 && ldx >= p, "boot_moments_f64: bad shape p=%lld ldx=%lld", (long long)p, (long long)ldx);
-    if (N > 320)
-        return tall_os() ? boot_os_moments(X, N, p, ldx, coef, K, R, pivot, sum, sumsq, workspace, workspace_bytes,
+    if (use_other(N))
+        return use_os(N) ? boot_os_moments(X, N, p, ldx, coef, K, R, pivot, sum, sumsq, workspace, workspace_bytes,
                                            (cudaStream_t)stream)
                          : boot_rs_moments(X, N, p, ldx, coef, K, R, pivot, sum, sumsq, workspace, workspace_bytes,
                                            (cudaStream_t)stream);

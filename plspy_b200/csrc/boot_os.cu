@@ -27,16 +27,16 @@ namespace plsb {
 constexpr int OS_TM = 128;            // voxels per CTA tile
 constexpr int OS_TN = 96;             // columns per CTA tile
 constexpr int OS_NB = OS_TN / 8;      // 8-column blocks per tile
-constexpr int OS_KC = 32;             // rows of X per pipeline stage
-constexpr int OS_KS = OS_KC / 4;      // k-steps per stage
 constexpr int OS_PITCH = OS_TM + 4;   // doubles between consecutive rows of the A stage
-constexpr int OS_A_DOUBLES = OS_KC * OS_PITCH;
-constexpr int OS_B_DOUBLES = OS_KS * OS_NB * 32;
-constexpr int OS_STAGE_DOUBLES = OS_A_DOUBLES + OS_B_DOUBLES;      // 58 368 bytes
-constexpr int OS_NSTAGE = 3;
+// k-steps (of 4 rows) per pipeline stage: a template parameter KS in {5, 6, 7, 8}, chosen per design so that the row
+// count pads to whole stages with the least waste (N = 300: 75 k-steps = 15 stages of 5; N = 1200: 300 = 38 of 8 - 4)
+constexpr int os_a_doubles(int ks) { return 4 * ks * OS_PITCH; }
+constexpr int os_b_doubles(int ks) { return ks * OS_NB * 32; }
+constexpr int os_stage_doubles(int ks) { return os_a_doubles(ks) + os_b_doubles(ks); }       // 7296 ks bytes
+constexpr int os_nstage(int ks) { return (215 * 1024) / (os_stage_doubles(ks) * 8) > 6 ? 6 : (215 * 1024) / (os_stage_doubles(ks) * 8); }
 
 struct OsPlan {
-    int Kp, nacc, nb, nks, nct, nsplit, ct_per_split;
+    int Kp, nacc, nb, nks, ks, nct, nsplit, ct_per_split;
     size_t smem_bytes;
 };
 
@@ -50,9 +50,20 @@ static bool os_plan(int N, int K, int R, int64_t p, OsPlan& b) {
     }
     if (!best_kp) return false;
     b.Kp = best_kp; b.nacc = best_blk; b.nb = 8 * best_blk / best_kp;
-    b.nks = (int)cdiv(cdiv(N, 4), OS_KS) * OS_KS;
+    {
+        const int need = (int)cdiv(N, 4);
+        // padded k-steps are wasted DMMAs; shallower stages cost about 1.5 % per k-step below 8 (more barrier rounds
+        // per column tile: measured 0.85 vs 0.96 of the DGEMM peak between 5 and 8 k-steps per stage)
+        int best_ks = 8; double best_cost = 1e30;
+        for (int ks = 8; ks >= 5; --ks) {
+            const double cost = (double)((int)cdiv(need, ks) * ks - need) / need + 0.015 * (8 - ks);
+            if (cost < best_cost - 1e-12) { best_cost = cost; best_ks = ks; }
+        }
+        b.ks = best_ks;
+        b.nks = (int)cdiv(need, b.ks) * b.ks;
+    }
     b.nct = (int)cdiv((int64_t)R * b.Kp, OS_TN);
-    b.smem_bytes = (size_t)OS_NSTAGE * OS_STAGE_DOUBLES * sizeof(double) + 256;
+    b.smem_bytes = (size_t)os_nstage(b.ks) * os_stage_doubles(b.ks) * sizeof(double) + 256;
     // Split of the column tiles over CTAs that work on the SAME voxel tile (consecutive block indices, i.e. resident at
     // the same time).  A CTA re-streams its X tile (128 voxels x N rows = N KB) for every column tile; with one voxel
     // tile per SM the chip-wide working set is 148 N KB (180 MB at N = 1200) -- more than the L2 -- and every pass came
@@ -104,27 +115,30 @@ __global__ void __launch_bounds__(256) boot_os_pack_kernel(const double* __restr
     }
 }
 
-// Tile-major image of X: block (t, sb) = rows [32 sb, 32 sb + 32) x voxels [128 t, 128 t + 128) at a pitch of 132
+// Tile-major image of X: block (t, sb) = rows [4 ks sb, 4 ks (sb + 1)) x voxels [128 t, 128 t + 128) at a pitch of 132
 // doubles, zero-filled beyond N rows / p voxels (and in the 4 padding columns).  One pass over X per call
 // (3.5 ms for the 9.6 GB of BASELINE config 5, against 2.4 s of GEMM).
 __global__ void __launch_bounds__(256) os_ximage_kernel(const double* __restrict__ X, long long ldx, int N, long long p,
-                                                       int nsb, double* __restrict__ img) {
+                                                       int nsb, int ks, double* __restrict__ img) {
     const long long t = blockIdx.x;
     const int sb = blockIdx.y;
-    double* out = img + ((size_t)t * nsb + sb) * OS_A_DOUBLES;
-    for (int i = threadIdx.x; i < OS_A_DOUBLES; i += 256) {
+    const int a_doubles = 4 * ks * OS_PITCH;
+    double* out = img + ((size_t)t * nsb + sb) * a_doubles;
+    for (int i = threadIdx.x; i < a_doubles; i += 256) {
         const int r = i / OS_PITCH, c = i % OS_PITCH;
-        const int row = sb * OS_KC + r;
+        const int row = sb * 4 * ks + r;
         const long long v = t * OS_TM + c;
         out[i] = (c < OS_TM && row < N && v < p) ? __ldg(X + (long long)row * ldx + v) : 0.0;
     }
 }
 
-template <int NACC>
+template <int NACC, int KS>
 __global__ void __launch_bounds__(256, 1)
 boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
                        const double* __restrict__ coef, int nks, int nct, int ct_per_split, int R, int Kp, int K,
                        const double* __restrict__ pivot, double* __restrict__ osum, double* __restrict__ osumsq) {
+    constexpr int OS_KS = KS, OS_A_DOUBLES = os_a_doubles(KS), OS_B_DOUBLES = os_b_doubles(KS),
+                  OS_STAGE_DOUBLES = os_stage_doubles(KS), OS_NSTAGE = os_nstage(KS);
     extern __shared__ __align__(128) unsigned char smraw[];
     double* ring = reinterpret_cast<double*>(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)OS_NSTAGE * OS_STAGE_DOUBLES);
@@ -175,7 +189,7 @@ boot_moments_os_kernel(const double* __restrict__ Ximg, int N, long long p,
     const int nbp = 8 * NACC / Kp;             // resamples per period of 8 NACC columns
     // the two warps of an SM sub-partition (w and w + 4) run half a stage apart, so that one of them keeps the DMMA
     // pipe busy while the other folds a finished tile or waits at a stage boundary (as in boot_moments_kernel)
-    if (warp >= 4) __nanosleep((unsigned)(OS_KS * 24 * 8));
+    if (warp >= 4) __nanosleep((unsigned)(OS_KS * 24 * 8));      // ~ half a stage
     int slot = 0, prev_slot = 0, g = 0;
     uint32_t phase = 0, prev_phase = 0;
     for (int ct = ct0; ct < ct1; ++ct) {
@@ -287,23 +301,34 @@ __global__ void os_moments_reduce_kernel(const double* __restrict__ p1, const do
     sum[i] = a; sumsq[i] = b;
 }
 
-template <int NACC>
-static int os_launch(const OsPlan& b, const double* Ximg, int N, int64_t p, const double* coef, int K, int R,
-                     const double* pivot, double* o1, double* o2, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_os_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int NACC, int KS>
+static int os_launch_ks(const OsPlan& b, const double* Ximg, int N, int64_t p, const double* coef, int K, int R,
+                        const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(boot_moments_os_kernel<NACC, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)b.smem_bytes));
     dim3 grid((unsigned)(cdiv(p, OS_TM) * b.nsplit));
-    boot_moments_os_kernel<NACC><<<grid, 256, b.smem_bytes, st>>>(Ximg, N, p, coef, b.nks, b.nct, b.ct_per_split, R,
+    boot_moments_os_kernel<NACC, KS><<<grid, 256, b.smem_bytes, st>>>(Ximg, N, p, coef, b.nks, b.nct, b.ct_per_split, R,
                                                                  b.Kp, K, pivot, o1, o2);
     PLSB_LAUNCH_CHECK("boot_moments_os_kernel");
     return PLSB200_OK;
+}
+
+template <int NACC>
+static int os_launch(const OsPlan& b, const double* Ximg, int N, int64_t p, const double* coef, int K, int R,
+                     const double* pivot, double* o1, double* o2, cudaStream_t st) {
+    switch (b.ks) {
+        case 5: return os_launch_ks<NACC, 5>(b, Ximg, N, p, coef, K, R, pivot, o1, o2, st);
+        case 6: return os_launch_ks<NACC, 6>(b, Ximg, N, p, coef, K, R, pivot, o1, o2, st);
+        case 7: return os_launch_ks<NACC, 7>(b, Ximg, N, p, coef, K, R, pivot, o1, o2, st);
+        default: return os_launch_ks<NACC, 8>(b, Ximg, N, p, coef, K, R, pivot, o1, o2, st);
+    }
 }
 
 // (the image builder reads X with plain loads: no alignment requirement on X any more)
 bool boot_os_usable(const double*, int64_t, int64_t) { return true; }
 
 static size_t os_image_bytes(const OsPlan& b, int64_t p) {
-    return (size_t)cdiv(p, OS_TM) * (b.nks / OS_KS) * OS_A_DOUBLES * sizeof(double);
+    return (size_t)cdiv(p, OS_TM) * (b.nks / b.ks) * os_a_doubles(b.ks) * sizeof(double);
 }
 static size_t os_partial_bytes(const OsPlan& b, int64_t p, int K) {
     const size_t n = b.nsplit > 1 ? (size_t)2 * b.nsplit * p * K * sizeof(double) : 0;
@@ -355,8 +380,8 @@ int boot_os_moments(const double* X, int N, int64_t p, int64_t ldx, const double
     if (b.nsplit > 1) { o1 = (double*)base; o2 = o1 + (size_t)b.nsplit * p * K; }
     double* img = (double*)(base + pbytes);
     {
-        dim3 grid((unsigned)cdiv(p, OS_TM), (unsigned)(b.nks / OS_KS));
-        os_ximage_kernel<<<grid, 256, 0, st>>>(X, ldx, N, p, b.nks / OS_KS, img);
+        dim3 grid((unsigned)cdiv(p, OS_TM), (unsigned)(b.nks / b.ks));
+        os_ximage_kernel<<<grid, 256, 0, st>>>(X, ldx, N, p, b.nks / b.ks, b.ks, img);
         PLSB_LAUNCH_CHECK("os_ximage_kernel");
     }
     int rc;
