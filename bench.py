@@ -686,16 +686,32 @@ def run_gpu(args):
                     keep.clear()
                     for _ in range(2):
                         one_pass(Xh, Vh, sph, sbh, precision=m, totals=(tp, tb))
-                    e = timed(lambda: one_pass(Xh, Vh, sph, sbh, precision=m, totals=(tp, tb)), args.steps,
-                              f"solo_e2e_{m}", collective=False) / args.steps
-                    solo[m] = (v, e)
+                    hold = {}
+                    e = timed(lambda: hold.__setitem__("rt", one_pass(Xh, Vh, sph, sbh, precision=m, totals=(tp, tb))[1]),
+                              args.steps, f"solo_e2e_{m}", collective=False) / args.steps
+                    solo[m] = (v, e, hold["rt"])
         dist.barrier()
         if rank == 0:
             strong = {"workload": workload_name(GROUPS, C, p, nperm, nboot).replace(" per GPU", " IN TOTAL, sharded over "
                                                                                       f"{world} GPUs"),
                       "scaling": "strong", "n_gpus": world}
             for m in modes:
-                t1v, t1e = solo[m]
+                t1v, t1e, rt1 = solo[m]
+                rtn = sm[m]["rt"]             # the sharded run's results on rank 0 (same job, same index matrices)
+                lv = np.abs(s) > 1e-8
+
+                def mrel(a, b):
+                    a, b = np.asarray(a)[..., lv], np.asarray(b)[..., lv]
+                    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+                parity = {"against": "the same job on rank 0 alone (single-process path)",
+                          "p_values_equal": bool(np.array_equal(rtn.permute_ratio, rt1.permute_ratio)),
+                          "stepdown_equal": bool(np.array_equal(rtn.stepdown_ratio, rt1.stepdown_ratio)),
+                          "perm_s_hat_max_rel": mrel(rtn.perm_debug_dict["s_list"], rt1.perm_debug_dict["s_list"]),
+                          "std_errs_max_rel": mrel(rtn.std_errs, rt1.std_errs),
+                          "boot_ratios_max_rel": mrel(rtn.boot_ratios, rt1.boot_ratios),
+                          "conf_ints_max_abs": float(np.max(np.abs(rtn.conf_ints[0][:, lv] - rt1.conf_ints[0][:, lv])))}
+                parity["ok"] = bool(parity["p_values_equal"] and parity["stepdown_equal"]
+                                    and parity["perm_s_hat_max_rel"] < 1e-10 and parity["std_errs_max_rel"] < 1e-9)
                 rec = {"value": (tp + tb) / (sm[m]["ms_step"] * 1e-3), "unit": UNIT, "ms_per_step": sm[m]["ms_step"],
                        "e2e": {"value": (tp + tb) / (sm[m]["e2e_ms"] * 1e-3), "unit": UNIT,
                                "ms_per_step": sm[m]["e2e_ms"]},
@@ -704,6 +720,7 @@ def run_gpu(args):
                                                "how": "rank 0 alone, same process, other ranks idle"},
                        "efficiency": t1v / (world * sm[m]["ms_step"]),
                        "e2e_efficiency": t1e / (world * sm[m]["e2e_ms"]),
+                       "parity_vs_one_gpu": parity,
                        "phase_timeline_rank0": ph[m]}
                 strong["exact" if m == "fp64" else "fast"] = rec
     value = units_step / (ms_step * 1e-3)

@@ -616,6 +616,7 @@ class Engine:
         per = lib.plsb200_rb_boot_dmma_f64_workspace(N, p, K, 1, cs_host.ctypes.data, ncell, int(unit_cells),
                                                      int(want_t))
         if per and not getattr(self, "force_rb_fma", False):
+            self.last_rb_path = "dmma"
             nbt = max(1, min(R, int(max_ws_bytes // per)))
             ws_bytes = lib.plsb200_rb_boot_dmma_f64_workspace(N, p, K, nbt, cs_host.ctypes.data, ncell,
                                                               int(unit_cells), int(want_t))
@@ -630,6 +631,15 @@ class Engine:
                                                        self._p(ws), ws.numel(), self._stream()), "rb_boot_dmma_f64")
                 self._mark("rb_boot")
             return s1, s2, T, nrm2
+        # design outside the tensor-core kernel's buckets (more than 16 blocks or 384 rows after padding every block to a
+        # multiple of 4): the general FMA kernel is an order of magnitude slower -- say so once instead of silently
+        if not getattr(self, "force_rb_fma", False) and not getattr(Engine, "_warned_rb_fma", False):
+            import warnings
+            Engine._warned_rb_fma = True
+            warnings.warn(f"plspy_b200: behaviour / multiblock bootstrap with {ncell} blocks and {N} rows runs on the "
+                          "general FMA kernel (the DMMA kernel holds up to 16 blocks / 384 padded rows): expect ~10x "
+                          "less throughput", RuntimeWarning, stacklevel=3)
+        self.last_rb_path = "fma"
         cs = self.to_device(cs_host, I32)
         if T is None:
             T = self._empty(R, N, K)
