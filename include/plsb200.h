@@ -183,6 +183,14 @@ int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const d
  * rb_lvcorr: LVcorr[b] = _compute_corr(X_new @ V_hat, Y_new) (ncell*nb x K)  (bootstrap_permutation.py:636-642). */
 int plsb200_cell_standardize_f64(const double* X, int N, int64_t p, int64_t ldx, const int32_t* cell_start,
                                  int ncell, double* Xc, double* Z, void* stream);
+/* The N-space pass on the FP64 tensor cores (N <= 320, K <= 24): same outputs as plsb200_nspace_f64 from the PACKED
+ * coefficients of plsb200_boot_coef_pack_f64 (the tensor the exact bootstrap GEMM streams, so one pack serves both):
+ * H = G^T [C_1 | C_2 | ...] as a DMMA GEMM with G as the register-resident operand, d2 and T = Lmat H diag(1/sqrt(d2))
+ * from its epilogue.  T may be NULL (then Lmat NULL, Kt 0).  The workspace query returns 0 when the shape is not
+ * supported (use plsb200_nspace_f64).                                                                            */
+size_t plsb200_nspace_dmma_f64_workspace(int N, int K, int Kt, int R);
+int plsb200_nspace_dmma_f64(const double* G, int N, const double* Lmat, int Kt, const double* coef, int K, int R,
+                            double* d2, double* T, void* workspace, size_t workspace_bytes, void* stream);
 int plsb200_nspace_coef_f64(const double* G, int N, const double* C, int K, int R, const double* Lmat, int Kt,
                             double* d2, double* T, void* stream);
 /* B[r] = C_r^T G C_r (R x K x K) for explicit coefficients: the Gram matrix of a resampled behaviour / multiblock

@@ -47,6 +47,9 @@ SIGNATURES = {
                                c_size_t, c_void_p]),
     "plsb200_nspace_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p, c_int,
                                    c_double_p, c_double_p, c_void_p]),
+    "plsb200_nspace_dmma_f64_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "plsb200_nspace_dmma_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_double_p, c_int, c_int, c_double_p,
+                                        c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_nspace_gram_f64": (c_int, [c_double_p, c_int, c_double_p, c_int, c_int32_p, c_int, c_double_p, c_double_p,
                                         c_void_p]),
     "plsb200_perm_count_f64": (c_int, [c_double_p, c_int, c_int, c_double_p, c_double_p, c_double, c_double_p,

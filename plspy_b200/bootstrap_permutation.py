@@ -547,7 +547,10 @@ class _ResampleTestPLS(ResampleTest):
 
         lo, hi = dist.shard(niter)
         idx_dev = _index_shard(eng, indices, niter, lo, hi)
-        d2, Tdist = eng.nspace(E, idx_dev, Lmat=Abar)                       # Tdistrib (:633-634, :665-666)
+        # exact mode, single launch: the packed coefficients serve the N-space pass and the moment GEMM
+        packed = (eng.pack_coef(E, idx_dev) if (hi > lo and eng.precision == "fp64" and _early is None
+                                                and E.shape[1] <= eng.KMAX) else None)
+        d2, Tdist = eng.nspace(E, idx_dev, Lmat=Abar, packed=packed)        # Tdistrib (:633-634, :665-666)
         if pls_alg == "mct":
             XL = eng.xv(Vd)                                                 # X @ V once
             left = eng.uhat(XL, Lop, idx_dev)                               # U_hat (:617, :631)
@@ -566,7 +569,7 @@ class _ResampleTestPLS(ResampleTest):
         if _early is not None:
             s1, s2 = _early
         elif hi > lo:
-            s1, s2 = eng.boot_moments(E, idx_dev, pivot=numer)              # K4
+            s1, s2 = eng.boot_moments(E, idx_dev, pivot=numer, packed=packed)   # K4
         else:
             s1 = torch.zeros_like(numer); s2 = torch.zeros_like(numer)
         dist.allreduce_packed_([s1, s2])

@@ -90,39 +90,50 @@ static bool boot_plan(int N, int K, int R, int64_t p, BootPlan& b) {
 // coefficient packing: C_r = scatter(E, idx_r) written in B-fragment order.
 // offset(per, s, jb, lane) = ((per*nks + s)*nblk + jb)*32 + lane,  lane = 4*n + q,
 // column-in-period c = (r % nb)*Kp + k -> jb = c/8, n = c%8 ; row i -> s = i/4, q = i%4.
-// One CTA per resample; thread i scans idx for sources of target row i in index order (deterministic).
+// One CTA per PERIOD (nb resamples): thread i scans idx for sources of target row i in index order (deterministic),
+// the period's block is assembled in shared memory in fragment order and written out as one contiguous, coalesced
+// piece.  (Round 1 wrote every coefficient straight to its fragment position: 8-byte stores at a stride of
+// 256 nblk bytes, 25 % sector efficiency -- 0.42 ms for the 146 MB of the bench workload.)
 __global__ void __launch_bounds__(256) boot_coef_pack_kernel(const double* __restrict__ E, int N, int K,
-                                                            const int32_t* __restrict__ idx, int Kp, int nblk,
+                                                            const int32_t* __restrict__ idx, int R, int Kp, int nblk,
                                                             int nb, int nks, double* __restrict__ coef) {
     extern __shared__ __align__(16) double smp[];
-    double* Es = smp;                                   // [N][K]
-    int* ids = reinterpret_cast<int*>(Es + (size_t)N * K);
-    const int r = blockIdx.x;
-    const int32_t* my = idx + (size_t)r * N;
-    for (int i = threadIdx.x; i < N * K; i += blockDim.x) Es[i] = E[i];
-    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = my[i];
-    __syncthreads();
-    const int per = r / nb, cbase = (r % nb) * Kp;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        double acc[24];
+    const int stage_doubles = nks * nblk * 32;
+    double* blk = smp;                                  // [nks][nblk][32]
+    int* ids = reinterpret_cast<int*>(blk + stage_doubles);
+    int* start = ids + N; int* cur = start + N + 1; int* list = cur + N;
+    const int per = blockIdx.x;
+    for (int i = threadIdx.x; i < stage_doubles; i += blockDim.x) blk[i] = 0.0;
+    for (int slot = 0; slot < nb; ++slot) {
+        const int r = per * nb + slot;
+        if (r >= R) break;                              // ragged last period: the remaining slots stay zero
+        __syncthreads();                                // previous users of the lists are done (and blk is zeroed)
+        build_source_lists(idx + (size_t)r * N, N, ids, start, cur, list);
+        const int cbase = slot * Kp;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double acc[24];
 #pragma unroll
-        for (int k = 0; k < 24; ++k) acc[k] = 0.0;
-        for (int src = 0; src < N; ++src) {
-            if (ids[src] == i) {
+            for (int k = 0; k < 24; ++k) acc[k] = 0.0;
+            for (int t = start[i]; t < start[i + 1]; ++t) {
+                const int src = list[t];
 #pragma unroll
                 for (int k = 0; k < 24; ++k)
-                    if (k < K) acc[k] += Es[src * K + k];
+                    if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
             }
-        }
-        const int s = i >> 2, q = i & 3;
+            const int s = i >> 2, q = i & 3;
 #pragma unroll
-        for (int k = 0; k < 24; ++k) {
-            if (k < K) {
-                const int c = cbase + k;
-                coef[((size_t)(per * nks + s) * nblk + (c >> 3)) * 32 + 4 * (c & 7) + q] = acc[k];
+            for (int k = 0; k < 24; ++k) {
+                if (k < K) {
+                    const int c = cbase + k;
+                    blk[(s * nblk + (c >> 3)) * 32 + 4 * (c & 7) + q] = acc[k];
+                }
             }
         }
     }
+    __syncthreads();
+    double2* out = reinterpret_cast<double2*>(coef + (size_t)per * stage_doubles);
+    const double2* in = reinterpret_cast<const double2*>(blk);
+    for (int i = threadIdx.x; i < stage_doubles / 2; i += blockDim.x) out[i] = in[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,6 +288,160 @@ boot_moments_kernel(const double* __restrict__ X, long long ldx, int N, long lon
             o1[(vbase + rr) * K + k] = r1[rr * Kp + k];
             o2[(vbase + rr) * K + k] = r2[rr * Kp + k];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The N-space pass (K2/K6) on the same machinery: H = G^T [C_1 | C_2 | ...] is the bootstrap GEMM with the Gram
+// matrix as the data matrix (rows i, "voxels" j) and the same packed coefficient stream, and
+//     d2[r,k] = C_r[:,k]^T H[:,(r,k)],      T[r,c,k] = (Lmat G C_r)[c,k] / sqrt(d2[r,k])
+// come out of the epilogue: the data matrix is W = [G | 0 | (Lmat G)^T] (N rows x (Npad + Kt) columns, Npad = N rounded
+// up to 8), so a warp's 8 "voxels" are either rows of H -- its D fragment is multiplied element-wise with the
+// coefficients of those rows (read from the stage in shared memory), reduced over the 8 rows with shuffles and written
+// as one partial per (voxel group, resample, k) -- or rows of T, which are stored as they are.  Partials are summed in
+// a fixed order by nspace_finish_kernel (deterministic), which also applies 1/sqrt(d2) to T.
+// Replaces nspace_kernel (FMA, bound by the shared-memory pipe: profiles/ncu_nspace_r02.md) for N <= 320.
+struct NsArgs {
+    const double* W; long long ldw; int N, Nv, Npad;
+    const double* coef; int nper, per_per_split, nstage, R, Kp, K, Kt;
+    double* dpart;      // [ngH][R][K]
+    double* Traw;       // [R][Kt][K] or NULL
+};
+
+template <int NKS, int NBLK>
+__global__ void __launch_bounds__(BM_THREADS, 1) nspace_dmma_kernel(const NsArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int stage_doubles = NKS * NBLK * 32;
+    constexpr uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
+    double* ring = reinterpret_cast<double*>(smraw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.nstage * stage_doubles);
+    uint64_t* empty = full + a.nstage;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = lane & 3, vr = lane >> 2;
+    const int group = blockIdx.x * BM_WARPS + warp;          // 8 consecutive columns of W
+    const int v = group * 8 + vr;
+    const int per0 = blockIdx.y * a.per_per_split;
+    const int per1 = min(a.nper, per0 + a.per_per_split);
+    const int nit = per1 - per0;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, BM_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int it, int slot) {
+        mbar_expect_tx(full + slot, stage_bytes);
+        const char* src = reinterpret_cast<const char*>(a.coef + (size_t)(per0 + it) * stage_doubles);
+        char* dst = reinterpret_cast<char*>(ring + (size_t)slot * stage_doubles);
+#pragma unroll 1
+        for (uint32_t off = 0; off < stage_bytes; off += 16384u)
+            bulk_g2s(dst + off, src + off, min(16384u, stage_bytes - off), full + slot);
+    };
+    if (tid == 0)
+        for (int it = 0; it < min(a.nstage, nit); ++it) issue(it, it);
+
+    double x[NKS];
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        const int row = 4 * s + q;
+        x[s] = (row < a.N && v < a.Nv) ? __ldg(a.W + (long long)row * a.ldw + v) : 0.0;
+    }
+    const bool is_h = group * 8 < a.Npad;                    // warp-uniform: rows of H, else rows of T
+    const int nb = 8 * NBLK / a.Kp;
+    if (warp >= 4) __nanosleep((unsigned)(NKS * NBLK * 8));
+
+    int slot = 0, prev_slot = 0;
+    uint32_t phase = 0, prev_phase = 0;
+    for (int it = 0; it < nit; ++it) {
+        if (tid == 0 && it > 0) {
+            const int nx = it - 1 + a.nstage;
+            if (nx < nit) {
+                mbar_wait(empty + prev_slot, prev_phase);
+                issue(nx, prev_slot);
+            }
+        }
+        __syncwarp();
+        mbar_wait(full + slot, phase);
+        double d[NBLK][2];
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j) d[j][0] = d[j][1] = 0.0;
+        const volatile double* bs = ring + (size_t)slot * stage_doubles + lane;
+#pragma unroll
+        for (int s = 0; s < NKS; ++s) {
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j) {
+                const double b = bs[(s * NBLK + j) * 32];
+                dmma884(d[j][0], d[j][1], x[s], b);
+            }
+        }
+        // the coefficients of this thread's own row (v) for its columns: C[v, c] sits at k-step v/4, element v%4
+        double cv[NBLK][2];
+        if (is_h) {
+            const double* cs = ring + (size_t)slot * stage_doubles + (size_t)(v >> 2) * NBLK * 32 + (v & 3);
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) cv[j][e] = v < a.N ? cs[j * 32 + 4 * (2 * q + e)] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+
+        const int rbase = (per0 + it) * nb;
+        if (is_h) {
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double pr = cv[j][e] * d[j][e];
+                    pr += __shfl_xor_sync(0xffffffffu, pr, 4);
+                    pr += __shfl_xor_sync(0xffffffffu, pr, 8);
+                    pr += __shfl_xor_sync(0xffffffffu, pr, 16);
+                    const int c = 8 * j + 2 * q + e, r = rbase + c / a.Kp, k = c % a.Kp;
+                    if (vr == 0 && k < a.K && r < a.R) a.dpart[((size_t)group * a.R + r) * a.K + k] = pr;
+                }
+        } else if (a.Traw != nullptr) {
+            const int ci = v - a.Npad;
+#pragma unroll
+            for (int j = 0; j < NBLK; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * j + 2 * q + e, r = rbase + c / a.Kp, k = c % a.Kp;
+                    if (ci < a.Kt && k < a.K && r < a.R) a.Traw[((size_t)r * a.Kt + ci) * a.K + k] = d[j][e];
+                }
+        }
+        prev_slot = slot; prev_phase = phase;
+        if (++slot == a.nstage) { slot = 0; phase ^= 1u; }
+    }
+}
+
+// W = [G | 0 | (Lmat G)^T]: N rows, ldw columns
+__global__ void nspace_w_kernel(const double* __restrict__ G, int N, const double* __restrict__ Lmat, int Kt, int Npad,
+                                long long ldw, double* __restrict__ W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * ldw) return;
+    const int row = (int)(i / ldw), col = (int)(i % ldw);
+    double val = 0.0;
+    if (col < N) val = G[(size_t)row * N + col];
+    else if (col >= Npad && col - Npad < Kt) {
+        const double* l = Lmat + (size_t)(col - Npad) * N;
+        for (int t = 0; t < N; ++t) val = fma(l[t], G[(size_t)t * N + row], val);
+    }
+    W[i] = val;
+}
+
+// d2[r,k] = sum over the voxel groups (fixed order); T[r,c,k] *= 1/sqrt(d2[r,k])
+__global__ void nspace_finish_kernel(const double* __restrict__ dpart, int ngroups, int R, int K, int Kt,
+                                     double* __restrict__ d2, double* __restrict__ T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * K) return;
+    double s = 0.0;
+    for (int g = 0; g < ngroups; ++g) s += dpart[(size_t)g * R * K + i];
+    d2[i] = s;
+    if (T != nullptr) {
+        const double dn = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+        const int r = (int)(i / K), k = (int)(i % K);
+        for (int c = 0; c < Kt; ++c) T[((size_t)r * Kt + c) * K + k] *= dn;
     }
 }
 
@@ -460,10 +625,9 @@ extern "C" int plsb200_boot_coef_pack_f64(const double* E, int N, int K, const i
         return PLSB200_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * b.stage_doubles * sizeof(double), st));
-    size_t smem = (size_t)N * K * sizeof(double) + (size_t)N * sizeof(int);
+    size_t smem = b.stage_doubles * sizeof(double) + (size_t)(4 * N + 1) * sizeof(int);
     PLSB_CUDA(cudaFuncSetAttribute(boot_coef_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    boot_coef_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nblk, b.nb, b.nks, coef);
+    boot_coef_pack_kernel<<<b.nper, 256, smem, st>>>(E, N, K, idx, R, b.Kp, b.nblk, b.nb, b.nks, coef);
     PLSB_LAUNCH_CHECK("boot_coef_pack_kernel");
     return PLSB200_OK;
 }
@@ -567,5 +731,105 @@ extern "C" int plsb200_xv_f64(const double* X, int N, int64_t p, int64_t ldx, co
     PLSB_LAUNCH_CHECK("xv_partial_kernel");
     xv_reduce_kernel<<<(unsigned)cdiv((int64_t)N * K, 256), 256, 0, st>>>((const double*)workspace, nchunk, N * K, XL);
     PLSB_LAUNCH_CHECK("xv_reduce_kernel");
+    return PLSB200_OK;
+}
+
+// ---- N-space pass on DMMA (see nspace_dmma_kernel) -----------------------------------------------------------
+namespace plsb {
+struct NsLayout { int Npad, Nv, ngH; long long ldw; size_t off_w, off_dpart, total; };
+static NsLayout ns_layout(int N, int K, int Kt, int R) {
+    NsLayout L;
+    L.Npad = (N + 7) / 8 * 8;
+    L.Nv = L.Npad + Kt;
+    L.ldw = (L.Nv + 7) / 8 * 8;
+    L.ngH = L.Npad / 8;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    L.off_w = 0;
+    L.off_dpart = al((size_t)N * L.ldw * sizeof(double));
+    L.total = L.off_dpart + al((size_t)L.ngH * R * K * sizeof(double));
+    return L;
+}
+
+template <int NKS, int NBLK>
+static int ns_launch(const BootPlan& b, const NsArgs& a, int tiles, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(nspace_dmma_kernel<NKS, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)b.smem_bytes));
+    dim3 grid((unsigned)tiles, (unsigned)b.nsplit);
+    nspace_dmma_kernel<NKS, NBLK><<<grid, BM_THREADS, b.smem_bytes, st>>>(a);
+    PLSB_LAUNCH_CHECK("nspace_dmma_kernel");
+    return PLSB200_OK;
+}
+template <int NBLK>
+static int ns_dispatch(const BootPlan& b, const NsArgs& a, int tiles, cudaStream_t st) {
+    switch (b.nks) {
+#define PLSB_CASE(n) case n: return ns_launch<n, NBLK>(b, a, tiles, st);
+        PLSB_CASE(4) PLSB_CASE(8) PLSB_CASE(12) PLSB_CASE(16) PLSB_CASE(20) PLSB_CASE(24) PLSB_CASE(28)
+        PLSB_CASE(32) PLSB_CASE(36) PLSB_CASE(40) PLSB_CASE(44) PLSB_CASE(48) PLSB_CASE(52) PLSB_CASE(56)
+        PLSB_CASE(60) PLSB_CASE(64) PLSB_CASE(68) PLSB_CASE(72) PLSB_CASE(76) PLSB_CASE(80)
+#undef PLSB_CASE
+        default: set_err("nspace_dmma_f64: no kernel for nks=%d", b.nks); return PLSB200_EUNSUPPORTED;
+    }
+}
+}  // namespace plsb
+
+extern "C" size_t plsb200_nspace_dmma_f64_workspace(int N, int K, int Kt, int R) {
+    BootPlan b;
+    if (N > 320 || short_os() || Kt < 0 || !boot_plan(N, K, R, 1, b)) return 0;
+    return ns_layout(N, K, Kt, R).total;
+}
+
+extern "C" int plsb200_nspace_dmma_f64(const double* G, int N, const double* Lmat, int Kt, const double* coef, int K,
+                                       int R, double* d2, double* T, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    PLSB_CHECK_ARG(G && coef && d2 && workspace, "nspace_dmma_f64: null pointer");
+    PLSB_CHECK_ARG((T == nullptr && Kt == 0) || (T != nullptr && Lmat != nullptr && Kt > 0),
+                   "nspace_dmma_f64: T, Lmat and Kt go together");
+    PLSB_CHECK_ARG(N > 0 && K > 0 && R > 0, "nspace_dmma_f64: bad shape");
+    BootPlan b;
+    if (N > 320 || short_os() || !boot_plan(N, K, R, 1, b)) {
+        set_err("nspace_dmma_f64: unsupported shape N=%d K=%d (need N<=320, K<=24): use nspace_f64", N, K);
+        return PLSB200_EUNSUPPORTED;
+    }
+    const NsLayout L = ns_layout(N, K, Kt, R);
+    if (workspace_bytes < L.total) {
+        set_err("nspace_dmma_f64: workspace %zu < %zu bytes", workspace_bytes, L.total);
+        return PLSB200_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* W = (double*)((char*)workspace + L.off_w);
+    double* dpart = (double*)((char*)workspace + L.off_dpart);
+    {
+        const long long n = (long long)N * L.ldw;
+        nspace_w_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(G, N, Lmat, Kt, L.Npad, L.ldw, W);
+        PLSB_LAUNCH_CHECK("nspace_w_kernel");
+    }
+    // the grid: voxel tiles of 64 columns of W x splits of the period range that fill the SMs
+    const int tiles = (int)cdiv(L.Nv, BM_VOX);
+    {
+        const int nsm = num_sms();
+        int best = 1; double best_cost = 1e30;
+        for (int n = 1; n <= 64; ++n) {
+            if (n > 1 && b.nper / n < 4) break;
+            const double waves = (double)tiles * n / nsm;
+            const double cost = ceil(waves) / waves + 0.002 * (n - 1);
+            if (cost < best_cost - 1e-12) { best_cost = cost; best = n; }
+        }
+        b.per_per_split = (int)cdiv(b.nper, best);
+        b.nsplit = (int)cdiv(b.nper, b.per_per_split);
+    }
+    NsArgs a;
+    a.W = W; a.ldw = L.ldw; a.N = N; a.Nv = L.Nv; a.Npad = L.Npad; a.coef = coef; a.nper = b.nper;
+    a.per_per_split = b.per_per_split; a.nstage = b.nstage; a.R = R; a.Kp = b.Kp; a.K = K; a.Kt = Kt;
+    a.dpart = dpart; a.Traw = T;
+    int rc;
+    switch (b.nblk) {
+        case 1: rc = ns_dispatch<1>(b, a, tiles, st); break;
+        case 2: rc = ns_dispatch<2>(b, a, tiles, st); break;
+        default: rc = ns_dispatch<3>(b, a, tiles, st); break;
+    }
+    if (rc != PLSB200_OK) return rc;
+    const long long n = (long long)R * K;
+    nspace_finish_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(dpart, L.ngH, R, K, Kt, d2, T);
+    PLSB_LAUNCH_CHECK("nspace_finish_kernel");
     return PLSB200_OK;
 }

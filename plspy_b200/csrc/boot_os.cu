@@ -90,19 +90,19 @@ __global__ void __launch_bounds__(256) boot_os_pack_kernel(const double* __restr
                                                           const int32_t* __restrict__ idx, int Kp, int nks,
                                                           double* __restrict__ coef) {
     extern __shared__ int ids[];          // E (N x K) stays in global memory: L1/L2-resident, read via __ldg
+    int* start = ids + N; int* cur = start + N + 1; int* list = cur + N;
     const int r = blockIdx.x;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
-    __syncthreads();
+    build_source_lists(idx + (size_t)r * N, N, ids, start, cur, list);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         double acc[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc[k] = 0.0;
-        for (int src = 0; src < N; ++src)
-            if (ids[src] == i) {
+        for (int t = start[i]; t < start[i + 1]; ++t) {
+            const int src = list[t];
 #pragma unroll
-                for (int k = 0; k < 24; ++k)
-                    if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
-            }
+            for (int k = 0; k < 24; ++k)
+                if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
+        }
         const int s = i >> 2, q = i & 3;
 #pragma unroll
         for (int k = 0; k < 24; ++k)
@@ -354,7 +354,7 @@ int boot_os_pack(const double* E, int N, int K, const int32_t* idx, int R, doubl
         return PLSB200_EUNSUPPORTED;
     }
     PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nct * b.nks * OS_NB * 32 * sizeof(double), st));
-    boot_os_pack_kernel<<<R, 256, (size_t)N * sizeof(int), st>>>(E, N, K, idx, b.Kp, b.nks, coef);
+    boot_os_pack_kernel<<<R, 256, (size_t)(4 * N + 1) * sizeof(int), st>>>(E, N, K, idx, b.Kp, b.nks, coef);
     PLSB_LAUNCH_CHECK("boot_os_pack_kernel");
     return PLSB200_OK;
 }

@@ -88,20 +88,20 @@ __global__ void __launch_bounds__(256) boot_rs_pack_kernel(const double* __restr
                                                           const int32_t* __restrict__ idx, int Kp, int nacc, int nb,
                                                           int rs, int nks, int ck, int nsub, double* __restrict__ coef) {
     extern __shared__ int ids[];          // E (N x K) stays in global memory: L1/L2-resident, read via __ldg
+    int* start = ids + N; int* cur = start + N + 1; int* list = cur + N;
     const int r = blockIdx.x;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
-    __syncthreads();
+    build_source_lists(idx + (size_t)r * N, N, ids, start, cur, list);
     const int per = r / nb, cbase = (r % nb) * Kp;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         double acc[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc[k] = 0.0;
-        for (int src = 0; src < N; ++src)
-            if (ids[src] == i) {
+        for (int t = start[i]; t < start[i + 1]; ++t) {
+            const int src = list[t];
 #pragma unroll
-                for (int k = 0; k < 24; ++k)
-                    if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
-            }
+            for (int k = 0; k < 24; ++k)
+                if (k < K) acc[k] += __ldg(E + (size_t)src * K + k);
+        }
         const int rc = i / (4 * nks), s = (i % (4 * nks)) >> 2, q = i & 3;
         const int sub = s / ck, s_in = s % ck;
         const size_t base = ((((size_t)per * nsub + sub) * rs + rc) * ck + s_in) * nacc;
@@ -364,7 +364,7 @@ int boot_rs_pack(const double* E, int N, int K, const int32_t* idx, int R, doubl
         return PLSB200_EUNSUPPORTED;
     }
     PLSB_CUDA(cudaMemsetAsync(coef, 0, (size_t)b.nper * b.nsub * b.stage_doubles * sizeof(double), st));
-    size_t smem = (size_t)N * sizeof(int);
+    size_t smem = (size_t)(4 * N + 1) * sizeof(int);
     boot_rs_pack_kernel<<<R, 256, smem, st>>>(E, N, K, idx, b.Kp, b.nacc, b.nb, b.rs, b.nks, b.ck, b.nsub, coef);
     PLSB_LAUNCH_CHECK("boot_rs_pack_kernel");
     return PLSB200_OK;

@@ -140,15 +140,15 @@ __global__ void __launch_bounds__(CP_ROWS) coef_pack_tf32_kernel(const double* _
                                                                 float* __restrict__ img) {
     extern __shared__ __align__(16) double smp[];
     float* stg = reinterpret_cast<float*>(smp);                       // [2 planes][CP_KB][K][16]
-    int* ids = reinterpret_cast<int*>(stg + 2 * CP_KB * K * TF_KB);   // [N]
-    double* Esm = reinterpret_cast<double*>(ids + ((N + 1) & ~1));
+    int* ids = reinterpret_cast<int*>(stg + 2 * CP_KB * K * TF_KB);   // [N], then the ordered source lists
+    int* start = ids + N; int* cur = start + N + 1; int* list = cur + N;
+    double* Esm = reinterpret_cast<double*>(ids + ((4 * N + 2) & ~1));
     const double* Es = stage_e ? Esm : E;           // tall designs: E stays in global memory (L2-resident)
     const int r = blockIdx.x, tid = threadIdx.x;
     const int32_t* my = idx + (size_t)r * N;
     if (stage_e)
         for (int i = tid; i < N * K; i += CP_ROWS) Esm[i] = E[i];
-    for (int i = tid; i < N; i += CP_ROWS) ids[i] = my[i];
-    __syncthreads();
+    build_source_lists(my, N, ids, start, cur, list);          // (ends with a block barrier: Esm is staged too)
     const int ct = r / nres, nbase = (r % nres) * Kp;
     const size_t plane = (size_t)ntile * TF_KB;      // floats
     const int pstride = CP_KB * K * TF_KB;           // floats per staged plane
@@ -158,12 +158,11 @@ __global__ void __launch_bounds__(CP_ROWS) coef_pack_tf32_kernel(const double* _
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc[k] = 0.0;
         if (j < N) {
-            for (int src = 0; src < N; ++src) {
-                if (ids[src] == j) {
+            for (int t = start[j]; t < start[j + 1]; ++t) {
+                const int src = list[t];
 #pragma unroll
-                    for (int k = 0; k < 24; ++k)
-                        if (k < K) acc[k] += Es[src * K + k];
-                }
+                for (int k = 0; k < 24; ++k)
+                    if (k < K) acc[k] += Es[src * K + k];
             }
         }
         const int kbl = tid / TF_KB, jj = tid % TF_KB;
@@ -595,7 +594,7 @@ extern "C" int plsb200_boot_coef_pack_tf32(const double* E, int N, int K, const 
         return PLSB200_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t fixed = (size_t)2 * CP_KB * K * TF_KB * sizeof(float) + (size_t)((N + 1) & ~1) * sizeof(int);
+    const size_t fixed = (size_t)2 * CP_KB * K * TF_KB * sizeof(float) + (size_t)((4 * N + 2) & ~1) * sizeof(int);
     const int stage_e = (size_t)N * K * sizeof(double) + fixed <= 96 * 1024;
     const size_t smem = fixed + (stage_e ? (size_t)N * K * sizeof(double) : 0);
     PLSB_CHECK_ARG(smem <= 200 * 1024, "boot_coef_pack_tf32: N=%d too large", N);

@@ -177,6 +177,51 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* s
         : "memory");
 }
 
+// ---- ordered source lists of one resample (coefficient packs) ----
+// C_r = scatter(E, idx_r): target row i receives the rows E[src] of all sources with idx_r[src] == i, summed in increasing
+// src (the order fixes the rounding: deterministic and identical in every pack kernel).  The first packs let every
+// target thread scan all N sources -- O(N^2) dependent shared-memory reads per resample, the whole cost of a pack
+// (0.42-0.57 ms for 5000 resamples of 300 rows).  Here the block builds, per resample, a stable counting sort of the
+// sources by target: histogram (shared-memory atomics: counts are order-independent), exclusive prefix sum (warp 0),
+// stable fill (warp 0, 32 sources at a time in order: __match_any_sync ranks the lanes that share a target).
+// Afterwards list[start[i] .. start[i+1]) are the sources of target i in increasing order.
+// Shared memory: ids[N], start[N + 1], cur[N], list[N] ints.  All threads of the block must call it.
+__device__ __forceinline__ void build_source_lists(const int32_t* __restrict__ idx_row, int N, int* ids, int* start,
+                                                   int* cur, int* list) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int i = tid; i < N; i += nt) { ids[i] = idx_row[i]; cur[i] = 0; }
+    __syncthreads();
+    for (int i = tid; i < N; i += nt) atomicAdd(cur + ids[i], 1);
+    __syncthreads();
+    if (tid < 32) {
+        const int ch = (N + 31) / 32, b = lane * ch, e = min(N, b + ch);
+        int sum = 0;
+        for (int j = b; j < e; ++j) sum += cur[j];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        int run = incl - sum;
+        for (int j = b; j < e; ++j) { const int c = cur[j]; start[j] = run; cur[j] = run; run += c; }
+        if (lane == 31) start[N] = N;
+        __syncwarp();
+        for (int base = 0; base < N; base += 32) {
+            const int src = base + lane;
+            const bool valid = src < N;
+            const int key = valid ? ids[src] : -1 - lane;                  // (unique keys for the idle lanes)
+            const unsigned m = __match_any_sync(0xffffffffu, key);
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            if (valid) list[cur[key] + rank] = src;
+            __syncwarp();
+            if (valid && rank == __popc(m) - 1) cur[key] += rank + 1;     // the last lane of a group advances it
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
 // ---- Ampere-style cp.async with zero fill (SASS LDGSTS) ----
 template <int BYTES>
 __device__ __forceinline__ void cp_async_zfill(void* dst_smem, const void* src_gmem, int src_bytes) {

@@ -305,8 +305,27 @@ class Engine:
                                                    self._stream()), "nspace_coef_gram_f64")
         return B
 
-    def nspace(self, E, idx, Lmat=None):
-        """d2[r,k] = ||X^T C_r[:,k]||^2 and (optionally) T[r] = Lmat G C_r diag(1/sqrt(d2))."""
+    def pack_coef(self, E, idx):
+        """The per-resample coefficients C_r = scatter(E, idx_r) packed in the B-fragment order of the exact bootstrap
+        GEMM (one pack serves `boot_moments` and the tensor-core N-space pass).  Returns None when the shape has no
+        packed form (K > 24)."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        if K > self.KMAX or R == 0:
+            return None
+        with torch.cuda.device(self.device):
+            nbytes = lib.plsb200_boot_coef_bytes(self.N, K, R)
+            if nbytes == 0:
+                return None
+            coef = self._ws(nbytes)
+            check(lib.plsb200_boot_coef_pack_f64(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
+                                                 self._stream()), "boot_coef_pack_f64")
+        return {"coef": coef, "R": R, "K": K}
+
+    def nspace(self, E, idx, Lmat=None, packed=None):
+        """d2[r,k] = ||X^T C_r[:,k]||^2 and (optionally) T[r] = Lmat G C_r diag(1/sqrt(d2)).  Designs up to 320 rows
+        and 24 columns run on the FP64 tensor cores from the packed coefficients (`packed`: a `pack_coef` result to
+        reuse), the rest on the FMA kernel."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)
         R, K = int(idx.shape[0]), int(E.shape[1])
         assert idx.shape[1] == self.N and E.shape[0] == self.N
@@ -317,6 +336,19 @@ class Engine:
             assert Lmat.shape[1] == self.N
             T = self._empty(R, Kt, K)
         G = self.G
+        ws_bytes = lib.plsb200_nspace_dmma_f64_workspace(self.N, K, Kt, R) if R > 0 else 0
+        if ws_bytes and os.environ.get("PLSB200_NSPACE", "dmma") != "fma":
+            if packed is None or packed["R"] != R or packed["K"] != K:
+                packed = self.pack_coef(E, idx)
+            if packed is not None:
+                with torch.cuda.device(self.device):
+                    ws = self._ws(ws_bytes)
+                    self._mark("nspace")
+                    check(lib.plsb200_nspace_dmma_f64(self._p(G), self.N, self._p(Lmat), Kt, self._p(packed["coef"]), K,
+                                                      R, self._p(d2), self._p(T), self._p(ws), ws.numel(),
+                                                      self._stream()), "nspace_dmma_f64")
+                    self._mark("nspace")
+                return d2, T
         with torch.cuda.device(self.device):
             check(lib.plsb200_nspace_f64(self._p(G), self.N, self._p(E), K, self._p(idx), R, self._p(Lmat), Kt,
                                          self._p(d2), self._p(T), self._stream()), "nspace_f64")
@@ -439,8 +471,9 @@ class Engine:
 
     KMAX = 24   # columns per boot_moments launch
 
-    def boot_moments(self, E, idx, pivot=None):
-        """K4: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 with VS_r = X^T scatter(E, idx_r); p x K each."""
+    def boot_moments(self, E, idx, pivot=None, packed=None):
+        """K4: sum_r (VS_r - pivot), sum_r (VS_r - pivot)^2 with VS_r = X^T scatter(E, idx_r); p x K each.
+        `packed`: a `pack_coef` result for the same (E, idx) to reuse in the exact mode."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)
         R, K = int(idx.shape[0]), int(E.shape[1])
         if pivot is not None:
@@ -456,12 +489,11 @@ class Engine:
         if self.precision == "tf32x3":
             return self._boot_moments_tf32(E, idx, pivot, R, K)
         with torch.cuda.device(self.device):
-            nbytes = lib.plsb200_boot_coef_bytes(self.N, K, R)
-            if nbytes == 0:
+            if packed is None or packed["R"] != R or packed["K"] != K:
+                packed = self.pack_coef(E, idx)
+            if packed is None:
                 raise _lib.PlsB200Error(f"boot_moments: unsupported shape N={self.N} K={K} R={R}")
-            coef = self._ws(nbytes)
-            check(lib.plsb200_boot_coef_pack_f64(self._p(E), self.N, K, self._p(idx), R, self._p(coef),
-                                                 self._stream()), "boot_coef_pack_f64")
+            coef = packed["coef"]
             s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
             cur = torch.cuda.current_stream(self.device)
             for v0, v1, ev in self._x_ranges():          # one launch per voxel range still arriving, else one in all
