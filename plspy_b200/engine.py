@@ -56,7 +56,7 @@ class Engine:
 
     # ------------------------------------------------------------------ plumbing
     PIPELINED_UPLOAD_MIN_BYTES = 64 << 20
-    UPLOAD_CHUNKS = 4
+    UPLOAD_FIRST_VOXELS = 148 * 128      # first range of a pipelined upload: one full wave of 128-voxel tiles
 
     @property
     def X(self):
@@ -81,7 +81,7 @@ class Engine:
         return self._pending is not None
 
     def _upload_pipelined(self, Xh):
-        """Pinned host X -> device in UPLOAD_CHUNKS voxel ranges on a copy stream, one event per range, so that the
+        """Pinned host X -> device in two voxel ranges (see _start_upload) on a copy stream, one event per range, so that the
         voxel-tiled kernels (Gram partials, TF32 split, bootstrap moment GEMM) can start on the first range while
         the rest is still crossing PCIe.  The copies are only enqueued at the first use of X (`_start_upload`):
         host->device copies execute in issue order, so the small uploads of an analysis (index matrices, V, weights)
@@ -100,12 +100,21 @@ class Engine:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         side = self._copy_stream
         side.wait_stream(torch.cuda.current_stream(self.device))
-        step = -(-p // self.UPLOAD_CHUNKS)
-        step = -(-step // 256) * 256                  # whole pairs of 128-voxel tiles
+        # Exact mode -- two voxel ranges: a first one of one full wave of the FP64 moment GEMM (148 SMs x 128 voxels = whole
+        # waves of its 64-voxel tiles), whose GEMM (~20 ms) starts after ~1 ms of upload and covers the transfer of the
+        # rest; four equal ranges made four launches of 15.84 waves each, 0.65 waves = 2.2 ms of tail per analysis
+        # (e2e 222.0 -> 220.3 ms).  Fast mode -- four equal ranges: its GEMM takes 2.5 ms per tenth of X against 0.9 ms
+        # of upload, so a small first range would leave the GPU idle for most of the second range's transfer
+        # (measured: e2e 34.1 -> 36.8 ms with the two ranges of the exact mode).
+        if self.precision == "fp64":
+            first = self.UPLOAD_FIRST_VOXELS if p >= 4 * self.UPLOAD_FIRST_VOXELS else -(-(p // 2) // 256) * 256
+            bounds = [0, first, p] if 0 < first < p else [0, p]
+        else:
+            step = -(-(-(-p // 4)) // 256) * 256          # whole pairs of 128-voxel tiles
+            bounds = list(range(0, p, step)) + [p]
         pend = []
         with torch.cuda.device(self.device):
-            for v0 in range(0, p, step):
-                v1 = min(p, v0 + step)
+            for v0, v1 in zip(bounds[:-1], bounds[1:]):
                 # (torch's copy_ of a column block goes through a contiguous temporary and synchronises)
                 check(lib.plsb200_copy2d_h2d(Xd.data_ptr() + 8 * v0, 8 * p, Xh.data_ptr() + 8 * v0, 8 * p,
                                              8 * (v1 - v0), n, side.cuda_stream), "copy2d_h2d")
