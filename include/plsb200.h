@@ -305,12 +305,18 @@ int plsb200_split_svd_f64(const double* S11, const double* S12, const double* S2
  *    np.random.permutation(beh_rows) for the multiblock behaviour block (bootstrap_permutation.py:342-347).
  *  bootstrap_draws: count x N bootstrap index vectors; cond_order2 != NULL adds the independent behaviour-block
  *    draw of the multiblock methods (bootstrap_permutation.py:545-554).
- *  row_permutations: count x n, np.random.permutation(n) each (behaviour PLS, :337-340).                    */
+ *  row_permutations: count x n, np.random.permutation(n) each (behaviour PLS, :337-340).
+ *  split_draws: the draws of one split-half routine (plspy/core/split_half_resampling.py:136, 271, 282 and :555,
+ *    692, 703): `count` real splits of one permutation(group_sizes[g]) per group -> out_real (count x sum of sizes,
+ *    groups side by side), then `count` null splits of permutation(nsub) -> out_null_subj (count x nsub) followed by
+ *    permutation(n_rows) -> out_null_rows (count x n_rows).                                                  */
 int plsb200_host_task_permutations(uint32_t* key, int32_t* pos, const int32_t* cond_order, int G, int C,
                                    int beh_rows, int count, int32_t* out_task, int32_t* out_beh);
 int plsb200_host_bootstrap_draws(uint32_t* key, int32_t* pos, const int32_t* cond_order, int G, int C,
                                  const int32_t* cond_order2, int C2, int count, int32_t* out, int32_t* out2);
 int plsb200_host_row_permutations(uint32_t* key, int32_t* pos, int n, int count, int32_t* out);
+int plsb200_host_split_draws(uint32_t* key, int32_t* pos, const int32_t* group_sizes, int G, int nsub, int n_rows,
+                             int count, int32_t* out_real, int32_t* out_null_subj, int32_t* out_null_rows);
 
 #ifdef __cplusplus
 }

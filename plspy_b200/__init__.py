@@ -22,7 +22,7 @@ def __getattr__(name):
         from . import plugin
         return getattr(plugin, name)
     if name in ("io", "plugin", "bootstrap_permutation", "class_functions", "pls", "pls_classes", "resample",
-                "split_half_resampling", "engine", "dist", "build", "_lib"):
+                "split_half_resampling", "engine", "dist", "build", "_lib", "nifti", "device_analysis"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -110,6 +110,8 @@ SIGNATURES = {
     "plsb200_host_bootstrap_draws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                              c_void_p, c_void_p]),
     "plsb200_host_row_permutations": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "plsb200_host_split_draws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p]),
     "plsb200_salience_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,
                                      c_double_p, c_void_p]),
 }

@@ -176,3 +176,40 @@ extern "C" int plsb200_host_row_permutations(uint32_t* key, int32_t* pos, int n,
     *pos = mt.pos;
     return PLSB200_OK;
 }
+
+// Split-half draws (split_half_resampling.py:136 / :555 and :271, :282 / :692, :703; the two routines draw the same
+// sequence): `count` real splits of one np.random.permutation(n_g) per group, concatenated per split into
+// out_real (count x sum n_g), THEN `count` null splits of np.random.permutation(nsub) -> out_null_subj (count x nsub)
+// followed by np.random.permutation(n_rows) -> out_null_rows (count x n_rows).
+extern "C" int plsb200_host_split_draws(uint32_t* key, int32_t* pos, const int32_t* group_sizes, int G, int nsub,
+                                        int n_rows, int count, int32_t* out_real, int32_t* out_null_subj,
+                                        int32_t* out_null_rows) {
+    if (!check_state(key, pos) || !group_sizes || !out_real || !out_null_subj || !out_null_rows || G < 1 || nsub < 1 ||
+        n_rows < 1 || count < 0)
+        return PLSB200_EINVAL;
+    int S = 0;
+    for (int g = 0; g < G; ++g) {
+        if (group_sizes[g] < 1) return PLSB200_EINVAL;
+        S += group_sizes[g];
+    }
+    MT mt{key, *pos};
+    for (int r = 0; r < count; ++r) {
+        int32_t* o = out_real + (size_t)r * S;
+        for (int g = 0; g < G; ++g) {
+            const int n = group_sizes[g];
+            for (int i = 0; i < n; ++i) o[i] = i;
+            mt.shuffle(o, n);
+            o += n;
+        }
+    }
+    for (int r = 0; r < count; ++r) {
+        int32_t* a = out_null_subj + (size_t)r * nsub;
+        for (int i = 0; i < nsub; ++i) a[i] = i;
+        mt.shuffle(a, nsub);
+        int32_t* b = out_null_rows + (size_t)r * n_rows;
+        for (int i = 0; i < n_rows; ++i) b[i] = i;
+        mt.shuffle(b, n_rows);
+    }
+    *pos = mt.pos;
+    return PLSB200_OK;
+}

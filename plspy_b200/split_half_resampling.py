@@ -42,10 +42,20 @@ def draw_split_indices(pls_alg, cond_order, num_split, n_rows):
     permutation(n_g) per group (:136 / :555), then per null split permutation(total subjects) (:271 / :692)
     followed by permutation(n_rows) (rows of X for task methods :282 / :703, rows of Y otherwise)."""
     co = np.asarray(cond_order)
-    from . import dist
+    from . import dist, resample
     dist.assert_identical_rng("split-half indices")
-    real = [[np.random.permutation(co[g, 0]) for g in range(co.shape[0])] for _ in range(num_split)]
     nsub = n_rows // co.shape[1]
+    if resample.USE_NATIVE_RNG and num_split > 0:
+        # native generator continuing numpy's global stream (csrc/host_rng.cpp): same draws, same stream position
+        sizes = np.ascontiguousarray(co[:, 0], dtype=np.int32)
+        real = np.empty((num_split, int(sizes.sum())), dtype=np.int32)
+        subj = np.empty((num_split, nsub), dtype=np.int32)
+        rows = np.empty((num_split, n_rows), dtype=np.int32)
+        if resample._native("plsb200_host_split_draws", None, num_split, sizes.ctypes.data, len(sizes), nsub, n_rows,
+                            num_split, real.ctypes.data, subj.ctypes.data, rows.ctypes.data):
+            cuts = np.cumsum(sizes)[:-1]
+            return dict(real=[np.split(r, cuts) for r in real], null_subj=list(subj), null_rows=list(rows))
+    real = [[np.random.permutation(co[g, 0]) for g in range(co.shape[0])] for _ in range(num_split)]
     null_subj, null_rows = [], []
     for _ in range(num_split):
         null_subj.append(np.random.permutation(nsub))

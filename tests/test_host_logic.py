@@ -227,6 +227,31 @@ def test_native_index_generator_ragged_design_uses_numpy():
                                               out.ctypes.data, None) == -4
 
 
+@pytest.mark.parametrize("co,n_rows", [([[25] * 4] * 3, 300), ([[7] * 3, [9] * 3], 48), ([[1] * 2, [5] * 2], 12),
+                                       ([[6] * 4, [8] * 4], 56)])
+def test_native_split_half_draws_are_bit_identical_to_numpy(co, n_rows):
+    """split-half draws (split_half_resampling.py:136, 271, 282): same permutations and same stream position from the
+    native generator as from the np.random.permutation calls"""
+    from plspy_b200 import resample, split_half_resampling as sh
+    res = []
+    for native in (False, True):
+        resample.USE_NATIVE_RNG = native
+        try:
+            np.random.seed(99)
+            np.random.random(7)
+            d = sh.draw_split_indices("mct", np.array(co), 130, n_rows)
+            res.append((d, np.random.random(3)))
+        finally:
+            resample.USE_NATIVE_RNG = True
+    a, b = res[0][0], res[1][0]
+    assert len(a["real"]) == len(b["real"]) == 130
+    for x, y in zip(a["real"], b["real"]):
+        assert len(x) == len(y) and all(np.array_equal(u, v) for u, v in zip(x, y))
+    for k in ("null_subj", "null_rows"):
+        assert all(np.array_equal(u, v) for u, v in zip(a[k], b[k]))
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+
+
 def test_confidence_interval_matches_the_elementwise_loop():
     """plspy_b200.resample.confidence_interval (vectorised) against a restatement of the reference's element loop
     (resample.py:171-222: percentile positions 100 (k + 0.5) / B, np.interp, extremes clamped)"""
