@@ -159,6 +159,17 @@ int plsb200_boot_finalize_f64(const double* sum, const double* sumsq, int64_t p,
  * bootstrap_permutation.py:715,723,732)                                                             */
 int plsb200_colstd_f64(const double* A, int R, int64_t M, double* out, void* stream);
 
+/* ---- percentile interval over the resample axis (plspy/core/resample.py:171-222 `confidence_interval`, MATLAB
+ * prctile convention: sorted sample k at 100 (k + 0.5) / B per cent, linear interpolation, clamped to the extremes).
+ * Series s has its B samples at samples[r * stride_sample + s * stride_series] (strides in elements), so a
+ * (B x m x n) stack is stride_sample = m n, stride_series = 1.  q_lo / q_hi are fractions in [0, 1]; lower / upper
+ * receive nseries values each.  B <= 16384 sorts in shared memory; longer series need
+ * plsb200_percentile_f64_workspace(B) bytes of scratch.                                                      */
+size_t plsb200_percentile_f64_workspace(int B);
+int plsb200_percentile_f64(const double* samples, int B, int64_t nseries, int64_t stride_sample,
+                           int64_t stride_series, double q_lo, double q_hi, double* lower, double* upper,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- explicit saliences for a small batch: VS[r] = X^T . C_r  (R x p x K), for callers that ask for
  * boot_debug_dict["right_sv_sampled"] on problems small enough to hold it.                          */
 int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,

@@ -112,6 +112,9 @@ SIGNATURES = {
     "plsb200_host_row_permutations": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "plsb200_host_split_draws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p]),
+    "plsb200_percentile_f64_workspace": (c_size_t, [c_int]),
+    "plsb200_percentile_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_int64, c_double, c_double, c_double_p,
+                                       c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_salience_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,
                                      c_double_p, c_void_p]),
 }

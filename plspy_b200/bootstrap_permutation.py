@@ -427,6 +427,37 @@ class _ResampleTestPLS(ResampleTest):
             self.permute_ratio, self.stepdown_ratio, self.perm_debug_dict = perm_pending()
 
     # ------------------------------------------------------------------------------------------
+    def _default_conf(self, conf):
+        return ((1 - self.CI) / 2, 1 - (1 - self.CI) / 2) if conf is None else (float(conf[0]), float(conf[1]))
+
+    def percentile_conf_ints(self, conf=None):
+        """Percentile intervals of the design-side bootstrap distributions: what the reference's commented-out
+        `resample.confidence_interval(Tdistrib, conf=dist)` / `(left_sv_sampled, ...)` call sites compute
+        (bootstrap_permutation.py:713-731 with resample.py:171-222), next to the normal-theory `conf_ints` it returns.
+        conf: (lower, upper) fractions, default from CI.  Returns {name: (lower, upper)} for the distributions of this
+        method ("Tdistrib" for the task rows, "left_sv_sampled" for behaviour correlations / design saliences)."""
+        if self._engine is None or not hasattr(self, "boot_debug_dict"):
+            raise exceptions.MissingParameterError("percentile intervals need a bootstrap test (num_boot > 0)")
+        conf = self._default_conf(conf)
+        out = {}
+        for key in ("Tdistrib", "left_sv_sampled"):
+            if key in self.boot_debug_dict:
+                a = np.asarray(self.boot_debug_dict[key])
+                if a.ndim >= 2 and a.size:
+                    out[key] = tuple(self._engine.to_host(*self._engine.percentile_interval(a, conf)))
+        return out
+
+    def salience_percentile_intervals(self, conf=None, max_bytes=4 << 30):
+        """Percentile interval of every brain salience over the bootstrap samples (element-wise
+        `confidence_interval(right_sv_sampled)`), streamed in voxel chunks so the B x p x K cube the reference stores
+        (bootstrap_permutation.py:497, 626) never exists.  Task methods (mct, cst).  Returns (lower, upper), p x K."""
+        fn = getattr(getattr(self, "boot_debug_dict", None), "salience_percentiles", None)
+        if fn is None:
+            raise exceptions.NotImplementedError(
+                "salience percentile intervals are available for the task methods (mct, cst) after a bootstrap test")
+        return fn(self._default_conf(conf), max_bytes)
+
+    # ------------------------------------------------------------------------------------------
     @staticmethod
     def _permutation_test(X, Y, U, s, V, cond_order, mctype, niter, pls_alg, preprocess=None, contrast=None,
                           threshold=1e-12, bscan=None, Xbscan=None, Ybscan=None, indices=None, engine=None,
@@ -598,6 +629,11 @@ class _ResampleTestPLS(ResampleTest):
                                   "accumulates its moments on the fly instead of storing it")
             return eng.salience(E, _index_shard(eng, indices, niter, 0, niter)).cpu().numpy()
         debug.set_lazy("right_sv_sampled", _right)
+
+        def _salience_percentiles(conf, max_bytes=4 << 30):
+            lo_, hi_ = eng.salience_percentiles(E, _index_shard(eng, indices, niter, 0, niter), conf, max_bytes)
+            return tuple(eng.to_host(lo_, hi_))
+        debug.salience_percentiles = _salience_percentiles
         return conf_int, std_errs_h, boot_ratios_h, debug
 
     # ------------------------------------------------------------------------------------------

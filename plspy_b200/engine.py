@@ -537,6 +537,36 @@ class Engine:
             check(lib.plsb200_colstd_f64(self._p(A), R, M, self._p(out), self._stream()), "colstd_f64")
         return out
 
+    def percentile_interval(self, A, conf=(0.05, 0.95)):
+        """Element-wise percentile interval over the first axis of a (B x ...) stack (resample.py:171-222, MATLAB
+        prctile convention); returns (lower, upper) device tensors shaped like A[0]."""
+        A = self.to_device(A, F64)
+        B = int(A.shape[0]); M = int(A.numel() // B)
+        lo = self._empty(*A.shape[1:]); hi = self._empty(*A.shape[1:])
+        with torch.cuda.device(self.device):
+            nb = lib.plsb200_percentile_f64_workspace(B)
+            ws = self._ws(nb)
+            check(lib.plsb200_percentile_f64(self._p(A), B, M, M, 1, float(conf[0]), float(conf[1]), self._p(lo),
+                                             self._p(hi), self._p(ws), nb, self._stream()), "percentile_f64")
+        return lo, hi
+
+    def salience_percentiles(self, E, idx, conf=(0.05, 0.95), max_bytes=4 << 30):
+        """Percentile interval of every element of the bootstrap salience distribution VS[r] = X^T scatter(E, idx_r)
+        (what `confidence_interval(right_sv_sampled)` would give) without holding the R x p x K cube: voxel chunks
+        of at most `max_bytes` are made explicit (`salience`), reduced to their two bounds and dropped.
+        Returns (lower, upper), p x K device tensors."""
+        E = self.to_device(E, F64); idx = self.to_device(idx, I32)
+        R, K = int(idx.shape[0]), int(E.shape[1])
+        lo = self._empty(self.p, K); hi = self._empty(self.p, K)
+        vc = max(128, min(self.p, int(max_bytes // (R * K * 8)) // 128 * 128))
+        for v0 in range(0, self.p, vc):
+            v1 = min(self.p, v0 + vc)
+            cube = self.salience(E, idx, M=self.X[:, v0:v1])            # R x (v1 - v0) x K
+            l, h = self.percentile_interval(cube, conf)
+            lo[v0:v1] = l; hi[v0:v1] = h
+            del cube
+        return lo, hi
+
     def salience(self, E, idx, M=None):
         """Explicit VS[r] = M^T scatter(E, idx_r) (R x p x K), M = X by default -- small R only."""
         E = self.to_device(E, F64); idx = self.to_device(idx, I32)
