@@ -115,6 +115,19 @@ int plsb200_perm_count_f64(const double* d2, int R, int K, const double* s_ref, 
 int plsb200_uhat_f64(const double* XL, int64_t xl_stride, int N, int K, const double* Lop, int Ku,
                      const int32_t* idx, int R, double* Uhat, void* stream);
 
+/* ---- K1 fast mode: G = X X^T on the tcgen05 tensor cores (kind::tf32, 3xTF32 split), N <= 320 (else
+ * PLSB200_EUNSUPPORTED: use plsb200_gram_f64).  gram_tf32_split writes the operand image (TF32 hi/lo planes of X,
+ * [block of 16 voxels][hi|lo][row][16 voxels] in the K-major SWIZZLE_64B tile order; gram_tf32_image_bytes bytes);
+ * gram_tf32 forms G (N x N, both triangles) from it; accumulate != 0 adds to G (X given as several voxel ranges).
+ * p = the voxel count the image was built for.  Relative error of the diagonal ~3e-6 (FP32 accumulation in tensor
+ * memory drained every 512 voxels into round-to-nearest FP32 sums, FP64 across CTAs).  Replaces the N x p work of
+ * every permutation (plspy/core/bootstrap_permutation.py:323-452) like plsb200_gram_f64.                        */
+size_t plsb200_gram_tf32_image_bytes(int N, int64_t p);
+int plsb200_gram_tf32_split(const double* X, int N, int64_t p, int64_t ldx, void* image, void* stream);
+size_t plsb200_gram_tf32_workspace(int N, int64_t p);
+int plsb200_gram_tf32(const void* image, int N, int64_t p, double* G, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* ---- K4: bootstrap salience moments ---------------------------------------------------------------
  * The batched GEMM  VS[v, (r,k)] = sum_i X[i, v] . C_r[i, k]  over all R resamples, with
  * sum_r (VS - pivot) and sum_r (VS - pivot)^2 accumulated in registers; nothing of size p x K x R is

@@ -42,6 +42,10 @@ SIGNATURES = {
     "plsb200_gram_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_gram_stacked_f64": (c_int, [c_double_p, c_int, c_int64, c_double_p, c_int, c_int64, c_int64, c_double_p,
                                          c_void_p, c_size_t, c_void_p]),
+    "plsb200_gram_tf32_image_bytes": (c_size_t, [c_int, c_int64]),
+    "plsb200_gram_tf32_split": (c_int, [c_double_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "plsb200_gram_tf32_workspace": (c_size_t, [c_int, c_int64]),
+    "plsb200_gram_tf32": (c_int, [c_void_p, c_int, c_int64, c_double_p, c_int, c_void_p, c_size_t, c_void_p]),
     "plsb200_xv_f64_workspace": (c_size_t, [c_int, c_int64, c_int]),
     "plsb200_xv_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_double_p, c_void_p,
                                c_size_t, c_void_p]),

@@ -31,16 +31,23 @@ class Engine:
     (plspy/core/bootstrap_permutation.py:323-452, 537-675).
     """
 
-    PRECISIONS = ("fp64", "tf32x3")
+    PRECISIONS = ("fp64", "tf32x3", "tf32x3+gram")
+    GRAM_TF32_MAX_ROWS = 320
 
     def __init__(self, X, device=None, precision="fp64"):
         """precision: "fp64" (exact mode, FP64 DMMA) or "tf32x3" (fast mode: the bootstrap moment GEMM runs on the
         tcgen05 tensor cores with the 3xTF32 split; every N-space quantity -- Gram matrix, permutation p-values,
-        Tdistrib, U_hat -- stays FP64)."""
+        Tdistrib, U_hat -- stays FP64) or "tf32x3+gram" (fast mode whose Gram matrix G = X X^T is ALSO formed on the
+        tcgen05 tensor cores with the 3xTF32 split: permuted singular values then carry
+        a relative error of ~1e-6 instead of being exact, inside the fast mode's tolerance of 1e-5, and a permutation
+        p-value can differ by one count where a permuted value ties with the observed one at that level; designs
+        beyond 320 rows keep the exact Gram kernel)."""
         _require_cuda()
         if precision not in self.PRECISIONS:
             raise ValueError(f"precision must be one of {self.PRECISIONS}")
-        self.precision = precision
+        self.gram_tf32 = precision == "tf32x3+gram"
+        self.precision = "tf32x3" if self.gram_tf32 else precision
+        self._tf32_ranges = None
         self._ximage = None
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._pending = None          # [(v0, v1, event)]: voxel ranges of X still being uploaded (see _upload_x)
@@ -255,7 +262,9 @@ class Engine:
     def G(self):
         """G = X X^T (N x N), computed once per engine."""
         if self._G is None:
-            if self._pending is None:
+            if self.gram_tf32 and self.N <= self.GRAM_TF32_MAX_ROWS:
+                self._G = self._gram_tf32()
+            elif self._pending is None:
                 self._G = self.gram_of(self.X)
             else:       # partial Gram matrices of the voxel ranges as they arrive, summed in a fixed order
                 cur = torch.cuda.current_stream(self.device)
@@ -266,6 +275,27 @@ class Engine:
                     G = Gc if G is None else G.add_(Gc)
                 self._G = G
         return self._G
+
+    def _gram_tf32(self):
+        """K1 fast mode: G on the tcgen05 tensor cores, voxel range by voxel range as X arrives (TF32 split of a range
+        into the Gram kernel's operand image, then its partial Gram, accumulated in a fixed order)."""
+        G = self._empty(self.N, self.N)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            for i, (v0, v1, ev) in enumerate(self._x_ranges()):
+                if ev is not None:
+                    cur.wait_event(ev)
+                pc = v1 - v0
+                img = self._ws(lib.plsb200_gram_tf32_image_bytes(self.N, pc))
+                nb = lib.plsb200_gram_tf32_workspace(self.N, pc)
+                ws = self._ws(nb)
+                self._mark("gram_tf32")
+                check(lib.plsb200_gram_tf32_split(self._X.data_ptr() + 8 * v0, self.N, pc, self.ldx, self._p(img),
+                                                  self._stream()), "gram_tf32_split")
+                check(lib.plsb200_gram_tf32(self._p(img), self.N, pc, self._p(G), 1 if i else 0, self._p(ws), nb,
+                                            self._stream()), "gram_tf32")
+                self._mark("gram_tf32")
+        return G
 
     def gram_collective(self):
         """COLLECTIVE in a multi-process run (every rank must call it at the same point): G from the partial Gram
@@ -464,7 +494,7 @@ class Engine:
                                                   self._stream()), "boot_coef_pack_tf32")
             s1 = self._empty(self.p, K); s2 = self._empty(self.p, K)
             # the voxel ranges of the first call stay the unit of work for later calls (their images are cached)
-            if getattr(self, "_tf32_ranges", None) is None:
+            if self._tf32_ranges is None:
                 self._tf32_ranges = self._x_ranges()
             for i, (v0, v1, ev) in enumerate(self._tf32_ranges):
                 img = self._ximage_of(i, v0, v1, ev)         # split of range i, then straight away its GEMM

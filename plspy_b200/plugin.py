@@ -91,8 +91,8 @@ def install(plspy_module=None, precision="fp64"):
     """Route the permutation / bootstrap / split-half loops of `plspy_module` (default: `import plspy`) through the
     GPU engine.  Idempotent; returns the module.  `precision`: "fp64" (exact) or "tf32x3" (fast bootstrap GEMM)."""
     global _state
-    if precision not in ("fp64", "tf32x3"):
-        raise ValueError('precision must be "fp64" or "tf32x3"')
+    if precision not in ("fp64", "tf32x3", "tf32x3+gram"):
+        raise ValueError('precision must be "fp64", "tf32x3" or "tf32x3+gram"')
     if plspy_module is None:
         import plspy as plspy_module
     ref_bp = plspy_module.core.bootstrap_permutation

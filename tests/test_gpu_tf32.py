@@ -124,3 +124,54 @@ def test_boot_moments_tf32_corner_shapes(N, p, K, R):
     assert (np.abs(s1.cpu().numpy() - VS.sum(0)) / (R * colscale)).max() < 1e-5
     ref2 = (VS ** 2).sum(0)
     np.testing.assert_allclose(s2.cpu().numpy(), ref2, rtol=3e-5, atol=1e-5 * ref2.max())
+
+
+# ---- K1 fast mode: the Gram matrix on the tcgen05 tensor cores (csrc/gram_tf32.cu) ---------------------------
+@pytest.mark.parametrize("N,p,offset", [
+    (60, 1000, 0.0),        # one M tile, one CTA kind
+    (128, 4099, 0.0),       # exactly one M tile, ragged voxel count
+    (130, 513, 3.0),        # two M tiles (second: 2 rows), data with an offset (large positive sums everywhere)
+    (300, 20000, 0.0),      # the bench design: three M tiles, UMMA N = 256 + 48, two CTA kinds
+    (300, 200, 100.0),      # fewer voxel tiles than CTAs, fMRI-like offset
+    (320, 9000, 0.0),       # the row limit of the kernel
+    (37, 64, 0.0),          # tiny
+])
+def test_gram_tf32(N, p, offset):
+    """G = X X^T from the TF32 hi/lo image (MN-major operands, FP32 accumulation in tensor memory) against float64
+    numpy.  Tolerance: 1e-5 of sqrt(G_ii G_jj) (north star: singular values 1e-5 in the fast mode; measured ~3e-6 on
+    the diagonal, where the tensor core's truncating accumulation adds up)."""
+    from plspy_b200.engine import Engine
+    rs = np.random.RandomState(N + p)
+    X = rs.standard_normal((N, p)) + offset
+    eng = Engine(X, precision="tf32x3+gram")
+    G = eng.G.cpu().numpy()
+    ref = X @ X.T
+    d = np.sqrt(np.diag(ref))
+    assert (np.abs(G - ref) / (d[:, None] * d[None, :])).max() < 1e-5
+    assert np.array_equal(G, G.T)
+    eng2 = Engine(X, precision="tf32x3+gram")
+    assert np.array_equal(eng2.G.cpu().numpy(), G)                    # deterministic
+
+
+def test_gram_tf32_tall_design_uses_the_exact_kernel():
+    from plspy_b200.engine import Engine
+    X = np.random.RandomState(4).standard_normal((360, 700))
+    G = Engine(X, precision="tf32x3+gram").G.cpu().numpy()
+    np.testing.assert_allclose(G, X @ X.T, rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("case", ["mct_m0_bal", "mct_m1_unbal", "cst_bal"])
+def test_fast_mode_with_tf32_gram_against_reference_goldens(case):
+    """Whole path with precision="tf32x3+gram": permuted singular values within the fast mode's 1e-5, p-values within
+    one count of the reference's (a permuted value can tie with the observed one at the 1e-6 level), bootstrap
+    fields within 1e-4."""
+    from test_gpu_parity import _load, _run_product
+    g = _load(case)
+    res = _run_product(g, precision="tf32x3+gram")
+    rt = res.resample_tests
+    tol = 1.0 / (int(g["nperm"]) + 1) + 1e-12
+    assert np.abs(np.asarray(rt.permute_ratio, dtype=float) - g["permute_ratio"]).max() <= tol
+    live = np.abs(g["s"]) > 1e-8
+    np.testing.assert_allclose(rt.std_errs[:, live], g["std_errs"][:, live], rtol=1e-4)
+    np.testing.assert_allclose(rt.boot_ratios[:, live], g["boot_ratios"][:, live], rtol=1e-4)
+    np.testing.assert_allclose(rt.conf_ints[0][:, live], g["conf_lo"][:, live], rtol=1e-4, atol=1e-5)
