@@ -276,13 +276,13 @@ class Engine:
                 self._G = G
         return self._G
 
-    def _gram_tf32(self):
+    def _gram_tf32(self, ranges=None):
         """K1 fast mode: G on the tcgen05 tensor cores, voxel range by voxel range as X arrives (TF32 split of a range
         into the Gram kernel's operand image, then its partial Gram, accumulated in a fixed order)."""
         G = self._empty(self.N, self.N)
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            for i, (v0, v1, ev) in enumerate(self._x_ranges()):
+            for i, (v0, v1, ev) in enumerate(self._x_ranges() if ranges is None else ranges):
                 if ev is not None:
                     cur.wait_event(ev)
                 pc = v1 - v0
@@ -307,7 +307,11 @@ class Engine:
         if (self._G is None and size > 1 and self.p >= 4096 * size
                 and os.environ.get("PLSB200_SHARD_GRAM", "1") != "0"):
             cut = [(self.p * r // size) // 64 * 64 for r in range(size)] + [self.p]
-            G = self.gram_of(self.X[:, cut[rank]:cut[rank + 1]])
+            if self.gram_tf32 and self.N <= self.GRAM_TF32_MAX_ROWS:
+                self.X                                      # (the whole of X is on the device from here on)
+                G = self._gram_tf32([(cut[rank], cut[rank + 1], None)])
+            else:
+                G = self.gram_of(self.X[:, cut[rank]:cut[rank + 1]])
             dist.allreduce_sum_(G)
             self._G = G
         return self.G
