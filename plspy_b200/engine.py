@@ -150,6 +150,9 @@ class Engine:
         if (size == 1 and on_host and torch.is_tensor(X) and X.dim() == 2 and X.dtype == F64 and X.is_pinned()
                 and X.is_contiguous() and X.numel() * 8 >= self.PIPELINED_UPLOAD_MIN_BYTES):
             return self._upload_pipelined(X)
+        if (size == 1 and on_host and len(X.shape) == 2 and not torch.is_tensor(X) and X.dtype == np.float64
+                and X.flags.c_contiguous and X.nbytes >= self.PIPELINED_UPLOAD_MIN_BYTES and self.PAGEABLE_UPLOAD_THREADS > 1):
+            return self._upload_pageable(X)
         if size == 1 or not on_host or len(X.shape) != 2:
             return self.to_device(X, F64)
         n = int(X.shape[0])
@@ -158,6 +161,49 @@ class Engine:
         if part.shape[0] == 0:
             part = torch.zeros((0, int(X.shape[1])), dtype=F64, device=self.device)
         return dist.gather_rows(part, n, lo).contiguous()
+
+    PAGEABLE_UPLOAD_THREADS = int(os.environ.get("PLSB200_UPLOAD_THREADS", str(max(1, min(8, (os.cpu_count() or 2) // 2)))))
+    _staging = {}                    # pinned staging buffers, shared by the engines of a process
+
+    def _upload_pageable(self, X):
+        """A large PAGEABLE host matrix (what `PLS(X numpy, ...)` hands over).  The driver stages a pageable
+        host->device copy through its own pinned buffer on one host thread: 43 ms = 11 GB/s for the 480 MB of the bench
+        design, more than the whole fast-mode GEMM, and calling it from several threads or streams changes nothing (the
+        copies serialise: measured 43 ms with 1, 2, 4 and 8 threads).  Here the staging is done by this library: row
+        blocks are copied into two pinned buffers by a few threads (numpy's copy loop releases the GIL) and leave them
+        by asynchronous DMA, so the host copy of block i+1 overlaps the transfer of block i: 16 ms with 4 threads, 14 ms
+        with 8 (tools/time_upload.py)."""
+        import concurrent.futures
+        n, p = int(X.shape[0]), int(X.shape[1])
+        out = torch.empty((n, p), dtype=F64, device=self.device)
+        nt = max(1, self.PAGEABLE_UPLOAD_THREADS)
+        rows = max(1, (32 << 20) // (8 * p))                      # ~32 MB per block
+        key = (rows * p, str(self.device))
+        if key not in Engine._staging:
+            Engine._staging[key] = [torch.empty(rows * p, dtype=F64).pin_memory() for _ in range(2)]
+        bufs = Engine._staging[key]
+        side = getattr(self, "_copy_stream", None)
+        if side is None:
+            side = self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        side.wait_stream(cur)
+        free = [None, None]                                       # event after which a staging buffer may be refilled
+        with concurrent.futures.ThreadPoolExecutor(nt) as pool:
+            for b, r0 in enumerate(range(0, n, rows)):
+                r1 = min(n, r0 + rows)
+                buf = bufs[b % 2][:(r1 - r0) * p].view(r1 - r0, p)
+                if free[b % 2] is not None:
+                    free[b % 2].synchronize()
+                dst = buf.numpy()
+                cuts = [r0 + (r1 - r0) * i // nt for i in range(nt + 1)]
+                list(pool.map(lambda i: np.copyto(dst[cuts[i] - r0:cuts[i + 1] - r0], X[cuts[i]:cuts[i + 1]]), range(nt)))
+                with torch.cuda.stream(side):
+                    out[r0:r1].copy_(buf, non_blocking=True)
+                    free[b % 2] = torch.cuda.Event()
+                    free[b % 2].record(side)
+        cur.wait_stream(side)
+        out.record_stream(side)
+        return out
 
     def to_device(self, a, dtype):
         if torch.is_tensor(a):

@@ -8,6 +8,7 @@ the reference uses (`ResampleTest._create`, `split_half_resampling.split_half*`)
 U and V "to be consistent with matlab" (:323).
 """
 import abc
+import os
 
 import numpy as np
 
@@ -129,12 +130,65 @@ class PLSBase(abc.ABC):
         self.Xbscan = self.X[mask]
         self.Ybscan = self.Y[mask]
 
+    def _prefetch(self, upload):
+        """Single-process runs: while this thread does the one-off original analysis, a worker thread (i) uploads X
+        (`upload`: host analysis on a host matrix; the pageable copy and the LAPACK SVD both release the GIL) and
+        (ii) draws the resampling index matrices in the reference's order (permutations, then bootstraps:
+        bootstrap_permutation.py:323-355, 537-572) with the native generator, which releases the GIL too.  Nothing else
+        touches numpy's global stream before `_resample` collects the result, so the draws and the stream position are
+        the reference's.  Multi-process runs keep everything on the calling thread (the draw sites hold collectives)."""
+        from . import dist, resample
+        ek = self._engine_kwargs
+        if dist.world()[1] > 1 or (self.num_perm <= 0 and self.num_boot <= 0) or os.environ.get("PLSB200_PREFETCH", "1") == "0":
+            return
+        want_idx = (ek.get("perm_indices") is None and ek.get("boot_indices") is None and resample.USE_NATIVE_RNG
+                    and ek.get("rotate_method", 2) == 2)
+        want_eng = upload and ek.get("engine") is None
+        if not (want_idx or want_eng):
+            return
+        import concurrent.futures
+        import torch
+        from .engine import Engine
+        device = ek.get("device")
+        if device is None and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())     # (the current device is per thread)
+        xsrc = getattr(self, "_x_tensor", None)
+        xsrc = self.X if xsrc is None else xsrc
+        Y = getattr(self, "Y", None) if self.pls_alg in ("rb", "csb", "mb", "cmb") else None
+        multi = self.pls_alg in ("mb", "cmb")
+        bscan, Ybscan = (self.bscan, self.Ybscan) if multi else (None, None)
+
+        def work():
+            out = {}
+            if want_eng:
+                out["engine"] = Engine(xsrc, device=device, precision=ek.get("precision", "fp64"))
+            if want_idx:
+                if self.num_perm > 0:
+                    out["perm_indices"] = resample.permutation_indices(self.pls_alg, self.num_perm, self.cond_order, Y=Y,
+                                                                       bscan=bscan, Ybscan=Ybscan)
+                if self.num_boot > 0:
+                    out["boot_indices"] = resample.bootstrap_indices(self.pls_alg, self.num_boot, self.cond_order, Y=Y,
+                                                                     bscan=bscan, Ybscan=Ybscan)
+            return out
+        pool = concurrent.futures.ThreadPoolExecutor(1)
+        self._bg = pool.submit(work)
+        pool.shutdown(wait=False)
+
+    def _collect_prefetch(self):
+        bg = self.__dict__.pop("_bg", None)
+        if bg is not None:
+            for k, v in bg.result().items():          # (re-raises what the worker raised, e.g. invalid behaviour data)
+                if self._engine_kwargs.get(k) is None:
+                    self._engine_kwargs[k] = v
+
     def _device_analysis(self):
         """True when `analysis="device"` was requested: the one-off analysis then runs through the Gram matrix on the
-        GPU (device_analysis.py) and `self._engine_kwargs["engine"]` holds the engine with X."""
+        GPU (device_analysis.py) and `self._engine_kwargs["engine"]` holds the engine with X.  Also the point where
+        every constructor starts the background upload / index drawing (`_prefetch`)."""
         mode = self._engine_kwargs.get("analysis", "host")
         if mode not in ("host", "device"):
             raise ValueError('analysis must be "host" or "device"')
+        self._prefetch(upload=(mode == "host"))
         if mode == "host":
             return False
         if self._engine_kwargs.get("engine") is None:
@@ -145,6 +199,7 @@ class PLSBase(abc.ABC):
         return True
 
     def _resample(self, Y, mctype, preprocess, **kw):
+        self._collect_prefetch()
         V = getattr(self, "_V_dev", None)
         xt = getattr(self, "_x_tensor", None)
         if xt is not None and self._engine_kwargs.get("engine") is None and (self.num_perm > 0 or self.num_boot > 0):

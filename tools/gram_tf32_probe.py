@@ -1,4 +1,9 @@
-"""Development probe of gram_tf32_kernel: small structured X, prints G and the raw per-CTA partial blocks."""
+"""Development probe of gram_tf32_kernel: small structured X ("eye": one non-zero per row, "rand"), prints G next to
+X X^T and the raw per-CTA partial blocks.  This is the tool that showed that `tcgen05.mma.kind::tf32` with the transpose
+bits of the instruction descriptor set returns zeros on a 64-byte-swizzled operand.
+
+    PYTHONPATH=. python tools/gram_tf32_probe.py N p [eye|rand]
+"""
 import os as _os, sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import numpy as np, torch
@@ -22,7 +27,6 @@ check(lib.plsb200_gram_tf32(img.data_ptr(), N, p, G.data_ptr(), 0, ws.data_ptr()
 torch.cuda.synchronize()
 ref = X @ X.T
 Gh = G.cpu().numpy()
-print("env", {k: v for k, v in _os.environ.items() if k.startswith("PLSB200_GT")})
 print("max abs err", np.abs(Gh - ref).max(), "max ref", np.abs(ref).max(), "nonzero G", int((Gh != 0).sum()), "of", N * N)
 part = ws.view(-1, 128, 320).cpu().numpy()
 nz = np.argwhere(np.abs(part).sum(axis=(1, 2)) > 0).ravel()
