@@ -163,6 +163,7 @@ class Engine:
         return dist.gather_rows(part, n, lo).contiguous()
 
     PAGEABLE_UPLOAD_THREADS = int(os.environ.get("PLSB200_UPLOAD_THREADS", str(max(1, min(8, (os.cpu_count() or 2) // 2)))))
+    STAGING_BLOCK_BYTES = 32 << 20
     _staging = {}                    # pinned staging buffers, shared by the engines of a process
 
     def _upload_pageable(self, X):
@@ -177,11 +178,10 @@ class Engine:
         n, p = int(X.shape[0]), int(X.shape[1])
         out = torch.empty((n, p), dtype=F64, device=self.device)
         nt = max(1, self.PAGEABLE_UPLOAD_THREADS)
-        rows = max(1, (32 << 20) // (8 * p))                      # ~32 MB per block
-        key = (rows * p, str(self.device))
-        if key not in Engine._staging:
-            Engine._staging[key] = [torch.empty(rows * p, dtype=F64).pin_memory() for _ in range(2)]
-        bufs = Engine._staging[key]
+        rows = max(1, self.STAGING_BLOCK_BYTES // (8 * p))
+        bufs = Engine._staging.get("bufs")
+        if bufs is None or bufs[0].numel() < rows * p:            # one pair per process, grown when a row is longer
+            bufs = Engine._staging["bufs"] = [torch.empty(rows * p, dtype=F64).pin_memory() for _ in range(2)]
         side = getattr(self, "_copy_stream", None)
         if side is None:
             side = self._copy_stream = torch.cuda.Stream(device=self.device)

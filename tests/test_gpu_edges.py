@@ -176,3 +176,18 @@ def test_pinned_tensor_input_and_float32_storage():
     np.random.seed(3)
     host = plspy_b200.PLS(X64, gs, nc, num_perm=20, num_boot=20, pls_method="mct")      # host analysis on the numpy view
     np.testing.assert_array_equal(host.resample_tests.permute_ratio, ref.permute_ratio)
+
+
+@pytest.mark.parametrize("N,p,threads", [(7, 1000, 8), (300, 5000, 4), (33, 70001, 3), (2, 64, 2)])
+def test_staged_upload_of_a_pageable_matrix_is_exact(N, p, threads, monkeypatch):
+    """Engine._upload_pageable (pinned staging buffers filled by several host threads): forced onto small matrices --
+    fewer rows than threads, several blocks per staging buffer, odd widths -- and compared bit for bit"""
+    from plspy_b200.engine import Engine
+    X = np.random.RandomState(N + p).standard_normal((N, p))
+    monkeypatch.setattr(Engine, "PIPELINED_UPLOAD_MIN_BYTES", 1)
+    monkeypatch.setattr(Engine, "PAGEABLE_UPLOAD_THREADS", threads)
+    monkeypatch.setattr(Engine, "STAGING_BLOCK_BYTES", 64 * 1024)
+    for _ in range(2):                                   # second engine: staging buffers reused
+        eng = Engine(X)
+        assert np.array_equal(eng.X.cpu().numpy(), X)
+    np.testing.assert_allclose(eng.G.cpu().numpy(), X @ X.T, rtol=1e-12, atol=1e-10)
