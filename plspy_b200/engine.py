@@ -5,6 +5,7 @@ produced by the hand-written kernels of libplsb200.so.  There is no CPU path: co
 without a CUDA device raises.
 """
 import os
+import threading
 
 import numpy as np
 import torch
@@ -165,6 +166,7 @@ class Engine:
     PAGEABLE_UPLOAD_THREADS = int(os.environ.get("PLSB200_UPLOAD_THREADS", str(max(1, min(8, (os.cpu_count() or 2) // 2)))))
     STAGING_BLOCK_BYTES = 32 << 20
     _staging = {}                    # pinned staging buffers, shared by the engines of a process
+    _staging_lock = threading.Lock()
 
     def _upload_pageable(self, X):
         """A large PAGEABLE host matrix (what `PLS(X numpy, ...)` hands over).  The driver stages a pageable
@@ -174,6 +176,10 @@ class Engine:
         blocks are copied into two pinned buffers by a few threads (numpy's copy loop releases the GIL) and leave them
         by asynchronous DMA, so the host copy of block i+1 overlaps the transfer of block i: 16 ms with 4 threads, 14 ms
         with 8 (tools/time_upload.py)."""
+        with Engine._staging_lock:
+            return self._upload_pageable_locked(X)
+
+    def _upload_pageable_locked(self, X):
         import concurrent.futures
         n, p = int(X.shape[0]), int(X.shape[1])
         out = torch.empty((n, p), dtype=F64, device=self.device)
@@ -201,6 +207,9 @@ class Engine:
                     out[r0:r1].copy_(buf, non_blocking=True)
                     free[b % 2] = torch.cuda.Event()
                     free[b % 2].record(side)
+        for ev in free:                      # the staging buffers are shared: drained before anybody refills them
+            if ev is not None:
+                ev.synchronize()
         cur.wait_stream(side)
         out.record_stream(side)
         return out
