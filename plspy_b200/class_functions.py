@@ -127,13 +127,37 @@ def _behaviour_coefficients(Y, cond_order):
 
 
 def _compute_corr(X, Y, cond_order):
-    """Stacked per-block Pearson correlations (G*C*nb x p) (class_functions.py:185-247)."""
+    """Stacked per-block Pearson correlations (G*C*nb x p) (class_functions.py:185-247).
+
+    The reference z-scores every block of X element-wise (`scipy.stats.zscore`, `/ sqrt(n)`, `nan_to_num`: a dozen
+    single-threaded passes over the block) before the product with the z-scored behaviours.  The column scale commutes
+    with the product, so here a block costs its centred copy d = Xb - mean, one pass for sum(d^2) = n var and the
+    nb x n x p product, `R_c = (Yz_c^T d) / sqrt(sum d^2)` (0 where the column is constant: the reference's
+    nan -> 0), and the blocks of a wide X run on a few threads (numpy releases the GIL in all three steps).  At the
+    cfg-4 shape (mb, 120 x 200 000 behaviour rows) this one-off step was 0.46 s of a 2.0 s analysis."""
     starts, sizes = _cells(cond_order)
-    Xz, Yz = _block_zscore(X, cond_order), _block_zscore(Y, cond_order)
+    Yz = _block_zscore(Y, cond_order)
     nb = Y.shape[1]
+    X = np.asarray(X)
     R = np.empty((len(sizes) * nb, X.shape[1]))
-    for c, (s, n) in enumerate(zip(starts, sizes)):
-        R[c * nb:(c + 1) * nb] = Yz[s:s + n].T @ Xz[s:s + n]
+
+    def block(c):
+        s, n = starts[c], sizes[c]
+        d = X[s:s + n] - X[s:s + n].mean(axis=0)
+        ss = np.einsum("ij,ij->j", d, d)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / np.sqrt(ss)
+        inv[~np.isfinite(inv)] = 0.0
+        R[c * nb:(c + 1) * nb] = (Yz[s:s + n].T @ d) * inv
+
+    if X.shape[1] * max(sizes, default=0) >= (1 << 20) and len(sizes) > 1:
+        import concurrent.futures
+        import os
+        with concurrent.futures.ThreadPoolExecutor(min(len(sizes), max(1, (os.cpu_count() or 2) // 2))) as pool:
+            list(pool.map(block, range(len(sizes))))
+    else:
+        for c in range(len(sizes)):
+            block(c)
     return R
 
 
