@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PLSB200_ABI_VERSION 2
+#define PLSB200_ABI_VERSION 3
 
 #define PLSB200_OK 0
 #define PLSB200_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */

@@ -128,7 +128,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.restype = _res
     _f.argtypes = _args
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 if lib.plsb200_abi_version() != ABI_VERSION:
     raise ImportError(f"{LIB_PATH}: ABI version {lib.plsb200_abi_version()} != {ABI_VERSION}; rebuild")
 

@@ -22,7 +22,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(_lib.lib, n), f"{n} declared in plsb200.h but not exported by libplsb200.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in plspy_b200/_lib.py"
     assert set(_lib.SIGNATURES) == set(names)
-    assert _lib.lib.plsb200_abi_version() == 2
+    assert _lib.lib.plsb200_abi_version() == 3
 
 
 def test_argument_errors_are_reported_without_a_gpu():
