@@ -17,6 +17,7 @@
 // Columns are processed in passes of 8*NBLK (NBLK = 1, 2, 3 for K <= 8, 16, more); the running moments live in
 // shared memory so that the registers are free for up to 96 k-steps of X fragments (384 padded rows).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace plsb {
 
@@ -25,6 +26,8 @@ constexpr int RD_MAXKS = 96;
 struct RdPlan {
     int nks, nblk, kcp, npass, nstage, warps;   // warps: template bucket (8 or 16) = upper bound of the launch
     int ks_unit;                                // first k-step of the trailing unit cells
+    int nstd;                                   // standardised cells (the cells before the trailing unit cells)
+    bool md;                                    // block moments on the tensor cores, 8 bootstraps at a time (see rb_vs_kernel)
     size_t stage_doubles;        // packed coefficients + weights of one bootstrap and one pass
     size_t smem_bytes;
     int krow[RD_MAXKS * 4];      // k-step slot -> row of Xc (-1 = padding)
@@ -59,10 +62,25 @@ static bool rd_plan(int N, int K, const int32_t* cs, int ncell, int unit_cells, 
     r.npass = (int)cdiv(K, r.kcp);
     r.stage_doubles = (size_t)r.nks * r.nblk * 32 + (size_t)r.nks * 4;
     r.warps = r.nks <= 32 ? 16 : 8;
-    // weight ring (4 slots), block sizes, running moments, per-warp scale / moment tables, barriers
-    const size_t fixed = ((size_t)4 * r.nks * 4 + 16 + 3 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 24) * sizeof(double) + 256;
+    r.nstd = ncell - unit_cells;
     const size_t coef_bytes = (size_t)r.nks * r.nblk * 32 * sizeof(double);
-    int ns = (int)((225 * 1024 - fixed) / coef_bytes);
+    static const char* const env = getenv("PLSB200_RB_MOMENTS");         // "fma" forces the scalar-moment kernel (A/B runs)
+    // moments on DMMA: weight fragments of one batch of 8 bootstraps, block sizes, running moments, per-warp scale tables
+    // of the batch ([8 bootstraps][standardised cell][8 voxels]), barriers
+    const size_t fixed_md = ((size_t)r.nks * 32 + 16 + 3 * r.nblk * 2 * r.warps * 32 + (size_t)r.warps * 64 * (r.nstd > 0 ? r.nstd : 1)) * sizeof(double) + 256;
+    int ns = (int)((225 * 1024 - (long long)fixed_md) / (long long)coef_bytes);
+    if (ns > 4) ns = 4;
+    // (only the 16-warp bucket: with 8 warps -- 2 per scheduler -- the serial moment phase of a batch is not covered by other
+    // warps; cfg 4 pass 2, 92 k-steps of which 30 standardised: 7.79 ms with the scalar moments, 8.41 ms with the DMMA moments)
+    r.md = ns >= 2 && r.nstd > 0 && r.warps == 16 && !(env && env[0] == 'f');
+    if (r.md) {
+        r.nstage = ns;
+        r.smem_bytes = ns * coef_bytes + fixed_md;
+        return true;
+    }
+    // scalar moments: weight ring (4 slots), block sizes, running moments, per-warp scale / moment tables, barriers
+    const size_t fixed = ((size_t)4 * r.nks * 4 + 16 + 3 * r.nblk * 2 * r.warps * 32 + r.warps * 16 * 24) * sizeof(double) + 256;
+    ns = (int)((225 * 1024 - (long long)fixed) / (long long)coef_bytes);
     if (ns > 4) ns = 4;
     if (ns < 2) return false;
     r.nstage = ns;
@@ -93,12 +111,26 @@ __global__ void rd_pack_kernel(const double* __restrict__ Q, const double* __res
     }
 }
 
+// multiplicity weights of a batch of 8 bootstraps as DMMA B fragments: [batch][nks][32], lane = 4*col + q holds the weight
+// of bootstrap 8*batch + col for row krow[4s + q] (0 for padding rows / bootstraps past the end)
+__global__ void rd_wpack_kernel(const double* __restrict__ W, int N, int b0, int nbt, const int* __restrict__ krow, int nks,
+                                double* __restrict__ wpack) {
+    const int batch = blockIdx.x;
+    double* out = wpack + (size_t)batch * nks * 32;
+    for (int i = threadIdx.x; i < nks * 32; i += blockDim.x) {
+        const int lane = i & 31, s = i >> 5;
+        const int bb = 8 * batch + (lane >> 2), row = krow[4 * s + (lane & 3)];
+        out[i] = (W && bb < nbt && row >= 0) ? W[(size_t)(b0 + bb) * N + row] : 0.0;
+    }
+}
+
 struct RdArgs {
     const double* Xc2;     // rows [n1, N) of the data matrix live here (row stride ld2); n1 == N: a single matrix
     long long ld2;
     int n1;
     const double* Xc;
     const double* pack;
+    const double* wpack;   // MD kernels: weight fragments per batch of 8 bootstraps
     const double* pivot;
     const int* krow;
     const double* celln;
@@ -109,6 +141,7 @@ struct RdArgs {
     long long p;
     int Kfull, k0, kc, nbt, npass, pass, nstage, ncell, nwarps;
     int ks_unit;       // first k-step of the trailing unit cells (plain linear rows: no block moments needed); nks if none
+    int nstd;          // standardised cells
     uint32_t cend[3];
 };
 
@@ -123,9 +156,23 @@ __device__ __forceinline__ double rd_scale(double m1, double m2, double n) {
     return (var > 1e-13 * m2 && var > 0.0) ? 1.0 / sqrt(var * n) : 0.0;
 }
 
+// MD path: the two scales a lane owns at the end of a cell (voxel vr, bootstraps 2q and 2q+1 of the batch).  Not inlined: it is
+// reached from every k-step of the unrolled moment loop and the FP64 sqrt / divide sequence should exist once.
+__device__ __noinline__ void rd_store_scales(double* dst0, double* dst1, double a10, double a20, double a11, double a21, double n) {
+    *dst0 = rd_scale(a10, a20, n);
+    *dst1 = rd_scale(a11, a21, n);
+}
+
 // W = warps per CTA: 8 (256 registers per thread: up to 96 k-steps of fragments) or 16 (128 registers: <= 32 k-steps,
 // twice the warps per scheduler to hide the serial phases between the DMMA bursts).
-template <int NKS, int NBLK, int W>
+// MD = block moments on the tensor cores.  The scalar version (MD = false) forms the weighted block moments of bootstrap b+1
+// with three FP64 operations per k-step in the shadow of the DMMAs of bootstrap b: on this GPU they share the FP64 pipe with
+// the DMMAs (ncu, profiles/ncu_rb_vs_r02.md: DADD + DMUL collect 34 % of the warp samples, DMMA 22 %; math-pipe throttle is the
+// top stall).  With MD the moments of EIGHT bootstraps are one DMMA chain per moment: D[voxel][bootstrap] += X-fragment x
+// weight-fragment (the multiplicity weights of the 8 bootstraps packed as a B fragment, rd_wpack_kernel), once per batch of 8
+// bootstraps -- 2 DMMAs + 1 DMUL per k-step and batch instead of 24 scalar operations and 8 quad reductions -- and the lane
+// that ends up with (voxel, bootstraps 2q, 2q+1) stores their two scales into the batch's scale table.
+template <int NKS, int NBLK, int W, bool MD>
 __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
     constexpr int RD_WARPS = W, RD_THREADS = W * 32;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -133,14 +180,17 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
     constexpr int w_doubles = NKS * 4;                            // its multiplicity weights, k-step order
     constexpr int pack_doubles = coef_doubles + w_doubles;        // layout of one (bootstrap, pass) in `pack`
     constexpr uint32_t coef_bytes = (uint32_t)coef_doubles * 8u, w_bytes = (uint32_t)w_doubles * 8u;
-    constexpr int WSLOTS = 4;
+    constexpr int WSLOTS = MD ? 1 : 4;
+    constexpr int w8_doubles = NKS * 32;                          // MD: weight fragments of one batch of 8 bootstraps
+    constexpr uint32_t w8_bytes = (uint32_t)w8_doubles * 8u;
+    const int nstd8 = a.nstd * 8;                                 // MD: scale-table entries per bootstrap of the batch
     double* ring = reinterpret_cast<double*>(smraw);              // [nstage][coef_doubles]
-    double* wring = ring + (size_t)a.nstage * coef_doubles;       // [WSLOTS][w_doubles]
-    double* celln = wring + WSLOTS * w_doubles;                   // [RD_MAXCELL] rows per cell (negative: unit cell)
+    double* wring = ring + (size_t)a.nstage * coef_doubles;       // [WSLOTS][w_doubles]   (MD: [w8_doubles])
+    double* celln = wring + (MD ? w8_doubles : WSLOTS * w_doubles);   // [RD_MAXCELL] rows per cell (negative: unit cell)
     double* acc = celln + RD_MAXCELL;                             // [2][NBLK*2][RD_THREADS] running moments
     double* pvs = acc + 2 * NBLK * 2 * RD_THREADS;                // [NBLK*2][RD_THREADS] pivot of this thread's elements
-    double* tabs = pvs + NBLK * 2 * RD_THREADS;                   // per warp: scale[16][8], then (m1, m2)[16][8]
-    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + RD_WARPS * RD_MAXCELL * 24);
+    double* tabs = pvs + NBLK * 2 * RD_THREADS;                   // per warp: scale[16][8], then (m1, m2)[16][8]  (MD: scale[8][nstd][8])
+    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + (MD ? (size_t)RD_WARPS * 8 * nstd8 : (size_t)RD_WARPS * RD_MAXCELL * 24));
     uint64_t* empty = full + a.nstage;
     uint64_t* wfull = empty + a.nstage;
 
@@ -173,8 +223,18 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
         bulk_g2s(wring + ws_ * w_doubles,
                  a.pack + (size_t)bb * bstride + (size_t)a.pass * pack_doubles + coef_doubles, w_bytes, wfull + ws_);
     };
+    auto issue_w8 = [&](int batch) {                              // MD: weight fragments of bootstraps 8 batch ... 8 batch + 7
+        mbar_expect_tx(wfull, w8_bytes);
+        const char* src = reinterpret_cast<const char*>(a.wpack + (size_t)batch * w8_doubles);
+        char* dst = reinterpret_cast<char*>(wring);
+#pragma unroll 1
+        for (uint32_t off = 0; off < w8_bytes; off += 16384u)
+            bulk_g2s(dst + off, src + off, min(16384u, w8_bytes - off), wfull);
+    };
     if (tid == 0) {
-        for (int bb = 0; bb < min(WSLOTS, a.nbt); ++bb) issue_w(bb);
+        if constexpr (MD) issue_w8(0);
+        else
+            for (int bb = 0; bb < min(WSLOTS, a.nbt); ++bb) issue_w(bb);
         for (int bb = 0; bb < min(a.nstage, a.nbt); ++bb) issue(bb, bb);
     }
 
@@ -201,15 +261,42 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
             // the fold's critical path, 5 % of the warp samples)
             myp[(2 * j + e) * RD_THREADS] = (live && a.pivot) ? __ldg(a.pivot + v * a.Kfull + a.k0 + c) : 0.0;
         }
-    double* sct = tabs + warp * (RD_MAXCELL * 24);                // scale[cell][voxel] of the current bootstrap
-    double* mt = sct + RD_MAXCELL * 8;                            // (m1, m2)[cell][voxel] of the next one
+    double* sct = MD ? tabs + (size_t)warp * 8 * nstd8            // MD: scale[bootstrap of the batch][cell][voxel]
+                     : tabs + warp * (RD_MAXCELL * 24);           // scale[cell][voxel] of the current bootstrap
+    double* mt = sct + RD_MAXCELL * 8;                            // (m1, m2)[cell][voxel] of the next one   (not MD)
     auto scales = [&]() {       // one (cell, voxel) pair per lane, no redundancy across the quad
         __syncwarp();
         for (int i = lane; i < a.ncell * 8; i += 32) sct[i] = rd_scale(mt[2 * i], mt[2 * i + 1], celln[i >> 3]);
         __syncwarp();
     };
+    // MD: moments and scales of a whole batch.  D fragment: row = voxel vr, columns 2q, 2q+1 = bootstraps of the batch.
+    auto batch_scales = [&](uint32_t parity) {
+        mbar_wait(wfull, parity);
+        const volatile double* wl = wring + lane;
+        double a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0};
+        int cell = 0;
+#pragma unroll
+        for (int s = 0; s < NKS; ++s) {
+            if (s < a.ks_unit) {                                  // warp-uniform
+                const double wf = wl[s * 32];
+                dmma884(a1[0], a1[1], x[s], wf);
+                dmma884(a2[0], a2[1], x[s] * x[s], wf);
+            }
+            if ((a.cend[s >> 5] >> (s & 31)) & 1u) {              // warp-uniform: last k-step of a cell
+                if (cell < a.nstd)
+                    rd_store_scales(sct + (2 * q) * nstd8 + cell * 8 + vr, sct + (2 * q + 1) * nstd8 + cell * 8 + vr,
+                                    a1[0], a2[0], a1[1], a2[1], celln[cell]);
+                ++cell;
+                a1[0] = a1[1] = a2[0] = a2[1] = 0.0;
+            }
+        }
+        __syncwarp();
+    };
 
     // ---- weighted block moments of bootstrap 0 (later bootstraps: inside the DMMA loop of their predecessor)
+    if constexpr (MD) {
+        batch_scales(0u);
+    } else {
     mbar_wait(wfull + 0, 0u);
     {
         const volatile double* ws = wring + q;
@@ -234,6 +321,7 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
         }
     }
     scales();
+    }
     if ((warp >> 2) & 1) __nanosleep((unsigned)(NKS * NBLK * 8));     // stagger the warps of a sub-partition (see boot.cu)
 
     int slot = 0, prev_slot = 0;
@@ -246,11 +334,20 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
             mbar_wait(empty + prev_slot, prev_phase);
             const int nx = bb - 1 + a.nstage;
             if (nx < a.nbt) issue(nx, prev_slot);
-            if (bb + WSLOTS - 1 < a.nbt) issue_w(bb + WSLOTS - 1);
+            if constexpr (MD) {
+                // every warp has finished iteration 8g, so it has also read the weights of batch g (before that iteration)
+                if ((bb & 7) == 1 && 8 * (bb / 8 + 1) < a.nbt) issue_w8(bb / 8 + 1);
+            } else {
+                if (bb + WSLOTS - 1 < a.nbt) issue_w(bb + WSLOTS - 1);
+            }
         }
         __syncwarp();
         const bool has_next = bb + 1 < a.nbt;
-        if (has_next) mbar_wait(wfull + (bb + 1) % WSLOTS, (uint32_t)(((bb + 1) / WSLOTS) & 1));
+        if constexpr (MD) {
+            if ((bb & 7) == 0 && bb > 0) batch_scales((uint32_t)((bb >> 3) & 1));
+        } else {
+            if (has_next) mbar_wait(wfull + (bb + 1) % WSLOTS, (uint32_t)(((bb + 1) / WSLOTS) & 1));
+        }
         mbar_wait(full + slot, phase);
         const volatile double* bs = ring + (size_t)slot * coef_doubles + lane;
         const volatile double* ws = wring + ((bb + 1) % WSLOTS) * w_doubles + q;     // (stale but harmless when !has_next)
@@ -263,7 +360,24 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
         double vs[NBLK][2], m1 = 0.0, m2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NBLK; ++j) vs[j][0] = vs[j][1] = 0.0;
-        {
+        if constexpr (MD) {
+            const double* scb = sct + (bb & 7) * nstd8 + vr;      // this bootstrap's scales of my voxel, one per cell
+            int cell = 0;
+            double sc = a.nstd > 0 ? scb[0] : 1.0;
+#pragma unroll
+            for (int s = 0; s < NKS; ++s) {
+                const double xs = x[s] * sc;
+#pragma unroll
+                for (int j = 0; j < NBLK; ++j) {
+                    const double b = bs[(s * NBLK + j) * 32];
+                    dmma884(vs[j][0], vs[j][1], xs, b);
+                }
+                if ((a.cend[s >> 5] >> (s & 31)) & 1u) {          // warp-uniform: last k-step of a cell
+                    ++cell;
+                    sc = cell < a.nstd ? scb[cell * 8] : 1.0;     // unit cells: plain rows; padding k-steps: x = 0
+                }
+            }
+        } else {
             int cell = 0;
             double sc = sct[vr];
 #pragma unroll
@@ -312,7 +426,8 @@ __global__ void __launch_bounds__(W * 32, 1) rb_vs_kernel(const RdArgs a) {
                     a.Npart[((size_t)bb * (8 * NBLK) + c) * ((size_t)gridDim.x * nwarps) + blockIdx.x * nwarps + warp] = n2;
                 if (a.VSt && ok) a.VSt[((size_t)bb * (8 * NBLK) + c) * a.p + v] = val;
             }
-        if (has_next) scales();                                   // scales of bootstrap bb+1 from its moments
+        if constexpr (!MD)
+            if (has_next) scales();                               // scales of bootstrap bb+1 from its moments
         prev_slot = slot; prev_phase = phase;
         if (++slot == a.nstage) { slot = 0; phase ^= 1u; }
     }
@@ -443,7 +558,7 @@ __global__ void rd_latent_reduce_kernel(const double* __restrict__ part, int nti
 }
 
 struct RdLayout {
-    size_t off_krow, off_celln, off_pack, off_vst, off_npart, off_gpart, total;
+    size_t off_krow, off_celln, off_pack, off_wpack, off_vst, off_npart, off_gpart, total;
     int ntile, nta, ntb, nsplit, nwarps;
     long long chunk;
 };
@@ -461,6 +576,7 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     L.off_krow = o; o = al(o + (size_t)r.nks * 4 * sizeof(int));
     L.off_celln = o; o = al(o + 16 * sizeof(double));
     L.off_pack = o; o = al(o + (size_t)nbt * r.npass * r.stage_doubles * sizeof(double));
+    L.off_wpack = o; o = al(o + (size_t)cdiv(nbt, 8) * r.nks * 32 * sizeof(double));
     L.nwarps = rd_balanced_warps(r.warps, p);
     L.ntile = (int)cdiv(p, L.nwarps * 8);
     L.off_vst = o; if (want_t) o = al(o + (size_t)nbt * r.kcp * p * sizeof(double));
@@ -478,12 +594,19 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     return L;
 }
 
-template <int NKS, int NBLK, int W>
-static int launch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
-    PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
-    rb_vs_kernel<NKS, NBLK, W><<<ntile, a.nwarps * 32, r.smem_bytes, st>>>(a);
+template <int NKS, int NBLK, int W, bool MD>
+static int launch_vs_md(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
+    PLSB_CUDA(cudaFuncSetAttribute(rb_vs_kernel<NKS, NBLK, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem_bytes));
+    rb_vs_kernel<NKS, NBLK, W, MD><<<ntile, a.nwarps * 32, r.smem_bytes, st>>>(a);
     PLSB_LAUNCH_CHECK("rb_vs_kernel");
     return PLSB200_OK;
+}
+template <int NKS, int NBLK, int W>
+static int launch_vs(const RdPlan& r, const RdArgs& a, int ntile, cudaStream_t st) {
+    if constexpr (W == 16) {
+        if (r.md) return launch_vs_md<NKS, NBLK, W, true>(r, a, ntile, st);
+    }
+    return launch_vs_md<NKS, NBLK, W, false>(r, a, ntile, st);
 }
 
 template <int NBLK>
@@ -552,9 +675,14 @@ extern "C" int plsb200_rb_boot_dmma_f64(const double* Xc, int N, int64_t p, cons
     PLSB_CUDA(cudaMemcpyAsync(d_celln, r.celln, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
     rd_pack_kernel<<<dim3(nbt, r.npass), 256, 0, st>>>(Q, W, N, K, b0, d_krow, r.nks, r.nblk, r.npass, d_pack);
     PLSB_LAUNCH_CHECK("rd_pack_kernel");
+    double* d_wpack = (double*)(ws + L.off_wpack);
+    if (r.md) {
+        rd_wpack_kernel<<<(unsigned)cdiv(nbt, 8), 256, 0, st>>>(W, N, b0, nbt, d_krow, r.nks, d_wpack);
+        PLSB_LAUNCH_CHECK("rd_wpack_kernel");
+    }
     for (int pass = 0; pass < r.npass; ++pass) {
         RdArgs a;
-        a.Xc = Xc; a.Xc2 = Xc2; a.n1 = n1; a.ld2 = ld2; a.pack = d_pack; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
+        a.Xc = Xc; a.Xc2 = Xc2; a.n1 = n1; a.ld2 = ld2; a.pack = d_pack; a.wpack = d_wpack; a.nstd = r.nstd; a.pivot = pivot; a.krow = d_krow; a.celln = d_celln; a.sum = sum; a.sumsq = sumsq;
         a.VSt = d_vst; a.Npart = d_npart; a.p = p; a.Kfull = K; a.k0 = pass * r.kcp;
         a.kc = K - a.k0 < r.kcp ? K - a.k0 : r.kcp;
         a.nbt = nbt; a.npass = r.npass; a.pass = pass; a.nstage = r.nstage; a.ncell = r.ncell; a.nwarps = L.nwarps; a.ks_unit = r.ks_unit;
