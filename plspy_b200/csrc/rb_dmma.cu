@@ -583,10 +583,19 @@ static RdLayout rd_layout(const RdPlan& r, int N, int64_t p, int nbt, bool want_
     L.off_npart = o; o = al(o + (size_t)L.ntile * L.nwarps * nbt * r.kcp * sizeof(double));
     L.nta = (int)cdiv(N, GN_T); L.ntb = (int)cdiv((int64_t)nbt * r.kcp, GN_T);
     const int64_t nk = cdiv(p, GN_KC);
-    int64_t ns = cdiv(4LL * num_sms(), (int64_t)L.nta * L.ntb);
     const int64_t max_ns = nk / 8 > 0 ? nk / 8 : 1;
-    if (ns > max_ns) ns = max_ns;
-    if (ns < 1) ns = 1;
+    // voxel splits: the grid (output tiles x splits) should fill whole waves of the 2 CTAs an SM holds.  The first version
+    // took ceil(4 SMs / tiles) splits: 70 tiles x 9 splits = 630 CTAs = 2.13 waves of 296 at the cfg-2 shape, i.e. a third
+    // wave for 13 % of the CTAs (13.8 ms = 0.59 of the DGEMM peak).  Now: the split count with the best wave efficiency,
+    // the smallest one among equals (fewer partial tiles to reduce).
+    const int64_t tiles = (int64_t)L.nta * L.ntb, slots = 2LL * num_sms();
+    int64_t ns = 1;
+    double best = -1.0;
+    for (int64_t c = 1; c <= max_ns && c <= 64; ++c) {
+        const double waves = (double)(tiles * c) / (double)slots;
+        const double eff = waves / ceil(waves);
+        if (eff > best + 0.02) { best = eff; ns = c; }
+    }
     L.chunk = cdiv(nk, ns) * GN_KC;
     L.nsplit = (int)cdiv(p, L.chunk);
     L.off_gpart = o; if (want_t) o = al(o + (size_t)L.nsplit * L.nta * L.ntb * GN_T * GN_T * sizeof(double));
