@@ -11,6 +11,7 @@
 // Only tiles with tj >= ti are computed; the reduce kernel mirrors them.  Split-K partials are summed
 // in a fixed order, so G is bit-reproducible run to run.
 #include "common.cuh"
+#include <math.h>
 
 namespace plsb {
 
@@ -32,12 +33,19 @@ static GramPlan gram_plan(int N, int64_t p) {
     g.ntile = (int)cdiv(N, GT);
     g.npair = g.ntile * (g.ntile + 1) / 2;
     int64_t nk = cdiv(p, GKC);
-    int64_t target = 4LL * num_sms();  // ~2 waves at 2 CTAs/SM
-    int64_t ns = cdiv(target, g.npair);
     int64_t max_ns = nk / 8 > 0 ? nk / 8 : 1;  // at least 8 k-stages per CTA
-    if (ns > max_ns) ns = max_ns;
-    if (ns < 1) ns = 1;
-    if (ns > 4096) ns = 4096;
+    if (max_ns > 4096) max_ns = 4096;
+    // voxel splits so that tile pairs x splits fills whole waves of the 2 CTAs an SM holds (the first version took
+    // ceil(4 SMs / pairs): 15 pairs x 40 splits = 600 CTAs = 2.03 waves of 296 at N = 300 -- a third wave for 8 CTAs);
+    // about two waves, the smallest count among (nearly) equally efficient ones
+    const int64_t slots = 2LL * num_sms();
+    int64_t ns = 1;
+    double best = -1.0;
+    for (int64_t c = 1; c <= max_ns && (double)(g.npair * c) <= 2.0 * slots + 0.5; ++c) {
+        const double waves = (double)(g.npair * c) / (double)slots;
+        const double eff = waves / ceil(waves);
+        if (eff > best + 0.02) { best = eff; ns = c; }
+    }
     g.chunk = cdiv(nk, ns) * GKC;
     g.nsplit = (int)cdiv(p, g.chunk);
     return g;
