@@ -47,6 +47,19 @@ def up_to_date():
     return open(STAMP).read().strip() == _source_hash()
 
 
+def _object_hash(src):
+    """Hash of everything one object file depends on: its source, the shared headers and the flags."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = [os.path.join(CSRC, src)] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "plsb200.h"))
+    for f in deps:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
@@ -55,17 +68,22 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(CSRC, os.path.splitext(s)[0] + ".o")
+        objs.append(o)
+        ostamp, want = o + ".srchash", _object_hash(s)
+        if not force and os.path.exists(o) and os.path.exists(ostamp) and open(ostamp).read().strip() == want:
+            continue                                       # this object is current: only changed sources are recompiled
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(o)
-    for s, pr in procs:
+        procs.append((s, ostamp, want, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, ostamp, want, pr in procs:
         out, _ = pr.communicate()
         if verbose or pr.returncode:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
+        with open(ostamp, "w") as f:
+            f.write(want)
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-lcudart"])
     with open(STAMP, "w") as f:
         f.write(_source_hash())

@@ -9,6 +9,7 @@
 // CTA = 128 voxels (thread per voxel in phase 1, 4 warps of DMMA row-tasks in phase 2); splits are looped inside the
 // CTA so the tile's rows of X stay hot in L2; per (tile, split) partials are summed in a fixed order afterwards.
 #include "common.cuh"
+#include <math.h>
 
 namespace plsb {
 
@@ -100,7 +101,10 @@ __global__ void __launch_bounds__(HG_VT) half_gram_win_kernel(const double* __re
     const long long v = (long long)blockIdx.x * HG_VT + tid;
     const bool ok = v < p;
     for (int i = tid; i < 2 * nseg * HG_SEG; i += HG_VT) sg[i] = segs[i];
-    for (int ss = 0; ss < ns; ++ss) {
+    // blockIdx.y = group of splits (the host picks the group count so that tiles x groups fills whole waves of CTAs)
+    const int per = (ns + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int ss_end = min(ns, ((int)blockIdx.y + 1) * per);
+    for (int ss = (int)blockIdx.y * per; ss < ss_end; ++ss) {
         const int sp = s0 + ss;
         for (int h = 0; h < 2; ++h) {
             __syncthreads();             // previous users of Qs / soff (and, for h == 0, of Rs) are done
@@ -183,20 +187,37 @@ __global__ void __launch_bounds__(HG_VT) half_gram_win_kernel(const double* __re
     }
 }
 
-// out[j] = sum over tiles of part[tile][j]  (fixed order)
-__global__ void hg_reduce_kernel(const double* __restrict__ part, int ntile, long long n, double* __restrict__ out) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// out[j] = sum over tiles of part[tile][j]  (fixed order).  A block takes 32 consecutive outputs (coalesced rows of the
+// partials) and splits the tiles over 8 thread rows, whose sums are combined in a fixed order: with one thread per
+// output and all tiles in sequence only half of the SMs had work (19 008 outputs at cfg 4) and each thread walked 1563
+// rows alone.
+constexpr int HGR_Y = 8;
+__global__ void __launch_bounds__(32 * HGR_Y) hg_reduce_kernel(const double* __restrict__ part, int ntile, long long n,
+                                                                double* __restrict__ out) {
+    __shared__ double red[HGR_Y][32];
+    const long long j = (long long)blockIdx.x * 32 + threadIdx.x;
+    const int y = threadIdx.y;
+    const int per = (ntile + HGR_Y - 1) / HGR_Y;
+    const int t0 = y * per, t1 = min(ntile, t0 + per);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int t = 0;
-    for (; t + 4 <= ntile; t += 4) {
-        a0 += part[(size_t)t * n + j];
-        a1 += part[(size_t)(t + 1) * n + j];
-        a2 += part[(size_t)(t + 2) * n + j];
-        a3 += part[(size_t)(t + 3) * n + j];
+    if (j < n) {
+        int t = t0;
+        for (; t + 4 <= t1; t += 4) {
+            a0 += part[(size_t)t * n + j];
+            a1 += part[(size_t)(t + 1) * n + j];
+            a2 += part[(size_t)(t + 2) * n + j];
+            a3 += part[(size_t)(t + 3) * n + j];
+        }
+        for (; t < t1; ++t) a0 += part[(size_t)t * n + j];
     }
-    for (; t < ntile; ++t) a0 += part[(size_t)t * n + j];
-    out[j] = (a0 + a1) + (a2 + a3);
+    red[y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (y == 0 && j < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < HGR_Y; ++k) s += red[k][threadIdx.x];
+        out[j] = s;
+    }
 }
 
 
@@ -232,8 +253,19 @@ extern "C" int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin,
                       (size_t)2 * nseg * HG_SEG * sizeof(int);                                                    \
         if (smem > 227 * 1024) { set_err("half_gram_win_f64: halves too large for shared memory"); return PLSB200_EUNSUPPORTED; } \
         PLSB_CUDA(cudaFuncSetAttribute(half_gram_win_kernel<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        half_gram_win_kernel<KCV><<<ntile, HG_VT, smem, st>>>(Xstd, Xlin, p, ids, Q, segs, nseg, nq, nmax, K, s0, \
-                                                              ns, (double*)workspace);                            \
+        int per_sm = 1;                                                                                           \
+        PLSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, half_gram_win_kernel<KCV>, HG_VT, smem)); \
+        /* groups of splits: a CTA keeps its voxel tile for a whole group; 1563 tiles on 592 slots are 2.64 waves, */ \
+        /* i.e. a third wave at 64 % -- with g groups the grid is g times longer and the tail g times shorter      */ \
+        const double slots = (double)num_sms() * (per_sm > 0 ? per_sm : 1);                                       \
+        int groups = 1;                                                                                           \
+        double best = -1.0;                                                                                       \
+        for (int c = 1; c <= ns && c <= 16; ++c) {                                                                \
+            const double waves = (double)ntile * c / slots, eff = waves / ceil(waves);                            \
+            if (eff > best + 0.02) { best = eff; groups = c; }                                                    \
+        }                                                                                                         \
+        half_gram_win_kernel<KCV><<<dim3(ntile, groups), HG_VT, smem, st>>>(Xstd, Xlin, p, ids, Q, segs, nseg, nq, \
+                                                                            nmax, K, s0, ns, (double*)workspace); \
     } while (0)
     if (K <= 8) PLSB_HGW_LAUNCH(8);
     else if (K <= 16) PLSB_HGW_LAUNCH(16);
@@ -245,7 +277,7 @@ extern "C" int plsb200_half_gram_win_f64(const double* Xstd, const double* Xlin,
 #undef PLSB_HGW_LAUNCH
     PLSB_LAUNCH_CHECK("half_gram_win_kernel");
     const long long n = (long long)ns * 3 * K * K;
-    hg_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const double*)workspace, ntile, n,
+    hg_reduce_kernel<<<(unsigned)cdiv(n, 32), dim3(32, HGR_Y), 0, st>>>((const double*)workspace, ntile, n,
                                                              S3 + (size_t)s0 * 3 * K * K);
     PLSB_LAUNCH_CHECK("hg_reduce_kernel");
     return PLSB200_OK;
