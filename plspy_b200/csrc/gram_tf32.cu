@@ -13,8 +13,9 @@
 //   * Only the upper block triangle is computed: M tile t (rows 128 t ...) against the columns 128 t ... N.  The
 //     accumulators of all M tiles of a 300-row design need 304 + 176 + 48 = 528 TMEM columns, 16 more than an SM
 //     has, so there are two kinds of CTAs: kind 0 owns M tile 0, kind 1 the remaining tiles (loading only the rows from
-//     128 on); the voxel blocks are divided among the CTAs of a kind, and the CTA counts of the two kinds are
-//     proportional to their column counts, so all CTAs finish together.
+//     128 on); the groups of 128 voxels are dealt round-robin to the CTAs of a kind -- both kinds sweep the image front to
+//     back at the same pace -- and the CTA counts of the two kinds are proportional to their column counts, so all CTAs
+//     finish together.
 //   * Precision: the tensor core truncates when it accumulates, which biases a long sum of like-signed terms (the
 //     diagonal of G) by ~3e-8 per accumulation step.  The TMEM accumulators are therefore drained every `dr` groups of
 //     128 voxels (192 accumulation steps at dr = 4) into a per-CTA FP32 partial block in global memory (L2-resident) with
