@@ -187,6 +187,10 @@ int plsb200_percentile_f64(const double* samples, int B, int64_t nseries, int64_
  * boot_debug_dict["right_sv_sampled"] on problems small enough to hold it.                          */
 int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
                          const int32_t* idx, int R, double* VS, void* stream);
+/* the same saliences series-major, VS[v][k][r] (p x K x R): the R samples of an element are contiguous, which is the
+ * layout plsb200_percentile_f64 sorts fastest (stride_sample = 1, stride_series = R); p <= 65535 * 128 per call.   */
+int plsb200_salience_series_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
+                                const int32_t* idx, int R, double* VS, void* stream);
 
 /* ---- K5: behaviour PLS (rb / csb) -----------------------------------------------------------------
  * Cells = (group, condition) blocks of consecutive rows, given as ncell+1 int32 offsets `cell_start`.

@@ -121,6 +121,8 @@ SIGNATURES = {
                                        c_double_p, c_void_p, c_size_t, c_void_p]),
     "plsb200_salience_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,
                                      c_double_p, c_void_p]),
+    "plsb200_salience_series_f64": (c_int, [c_double_p, c_int, c_int64, c_int64, c_double_p, c_int, c_int32_p, c_int,
+                                     c_double_p, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

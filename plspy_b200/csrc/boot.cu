@@ -469,18 +469,21 @@ __global__ void boot_finalize_kernel(const double* __restrict__ sum, const doubl
 
 // explicit saliences VS[r][v][k] = sum_i X[idx_r[i], v] . E[i, k]  (reference order of operations;
 // small problems / debugging only -- writes R*p*K doubles)
-template <int KT>
+// SERIES: output [v][k][r] (the R samples of an element contiguous: the layout percentile_kernel sorts fastest) with the
+// resample as the FAST grid index, so that the CTAs running at one time share their rows of X in L2 and write
+// neighbouring 8-byte slots of the same sectors.
+template <int KT, bool SERIES>
 __global__ void __launch_bounds__(128) salience_kernel(const double* __restrict__ X, int N, long long p, long long ldx,
                                                       const double* __restrict__ E, int K,
-                                                      const int32_t* __restrict__ idx, double* __restrict__ VS) {
+                                                      const int32_t* __restrict__ idx, int R, double* __restrict__ VS) {
     extern __shared__ __align__(16) double sms[];
     double* Es = sms;
     int* ids = reinterpret_cast<int*>(Es + (size_t)N * K);
-    const int r = blockIdx.y;
+    const int r = SERIES ? blockIdx.x : blockIdx.y;
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) Es[i] = E[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) ids[i] = idx[(size_t)r * N + i];
     __syncthreads();
-    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long v = (long long)(SERIES ? blockIdx.y : blockIdx.x) * blockDim.x + threadIdx.x;
     if (v >= p) return;
     for (int k0 = 0; k0 < K; k0 += KT) {
         double acc[KT];
@@ -494,7 +497,10 @@ __global__ void __launch_bounds__(128) salience_kernel(const double* __restrict_
         }
 #pragma unroll
         for (int t = 0; t < KT; ++t)
-            if (k0 + t < K) VS[((size_t)r * p + v) * K + k0 + t] = acc[t];
+            if (k0 + t < K) {
+                if (SERIES) VS[((size_t)v * K + k0 + t) * R + r] = acc[t];
+                else VS[((size_t)r * p + v) * K + k0 + t] = acc[t];
+            }
     }
 }
 
@@ -692,8 +698,21 @@ extern "C" int plsb200_boot_finalize_f64(const double* sum, const double* sumsq,
     return PLSB200_OK;
 }
 
+static int salience_launch(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K, const int32_t* idx, int R,
+                           double* VS, bool series, void* stream);
+
 extern "C" int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
                                     const int32_t* idx, int R, double* VS, void* stream) {
+    return salience_launch(X, N, p, ldx, E, K, idx, R, VS, false, stream);
+}
+
+extern "C" int plsb200_salience_series_f64(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K,
+                                           const int32_t* idx, int R, double* VS, void* stream) {
+    return salience_launch(X, N, p, ldx, E, K, idx, R, VS, true, stream);
+}
+
+static int salience_launch(const double* X, int N, int64_t p, int64_t ldx, const double* E, int K, const int32_t* idx, int R,
+                           double* VS, bool series, void* stream) {
     PLSB_CHECK_ARG(X && E && idx && VS, "salience_f64: null pointer");
     PLSB_CHECK_ARG(N > 0 && p > 0 && K > 0 && R >= 0 && ldx >= p, "salience_f64: bad shape");
     if (R == 0) return PLSB200_OK;
@@ -702,9 +721,17 @@ extern "C" int plsb200_salience_f64(const double* X, int N, int64_t p, int64_t l
         set_err("salience_f64: N*K too large");
         return PLSB200_EUNSUPPORTED;
     }
-    PLSB_CUDA(cudaFuncSetAttribute(salience_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)cdiv(p, 128), (unsigned)R);
-    salience_kernel<12><<<grid, 128, smem, (cudaStream_t)stream>>>(X, N, p, ldx, E, K, idx, VS);
+    if (series) {
+        PLSB_CHECK_ARG(cdiv(p, 128) <= 65535, "salience_series_f64: more than 65535 voxel blocks per call");
+        PLSB_CUDA(cudaFuncSetAttribute(salience_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)R, (unsigned)cdiv(p, 128));
+        salience_kernel<12, true><<<grid, 128, smem, (cudaStream_t)stream>>>(X, N, p, ldx, E, K, idx, R, VS);
+    } else {
+        PLSB_CHECK_ARG(R <= 65535, "salience_f64: more than 65535 resamples per call");
+        PLSB_CUDA(cudaFuncSetAttribute(salience_kernel<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)cdiv(p, 128), (unsigned)R);
+        salience_kernel<12, false><<<grid, 128, smem, (cudaStream_t)stream>>>(X, N, p, ldx, E, K, idx, R, VS);
+    }
     PLSB_LAUNCH_CHECK("salience_kernel");
     return PLSB200_OK;
 }

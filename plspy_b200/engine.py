@@ -648,12 +648,21 @@ class Engine:
         R, K = int(idx.shape[0]), int(E.shape[1])
         lo = self._empty(self.p, K); hi = self._empty(self.p, K)
         vc = max(128, min(self.p, int(max_bytes // (R * K * 8)) // 128 * 128))
-        for v0 in range(0, self.p, vc):
-            v1 = min(self.p, v0 + vc)
-            cube = self.salience(E, idx, M=self.X[:, v0:v1])            # R x (v1 - v0) x K
-            l, h = self.percentile_interval(cube, conf)
-            lo[v0:v1] = l; hi[v0:v1] = h
-            del cube
+        X = self.X
+        nb = lib.plsb200_percentile_f64_workspace(R)
+        with torch.cuda.device(self.device):
+            ws = self._ws(nb)
+            for v0 in range(0, self.p, vc):
+                v1 = min(self.p, v0 + vc)
+                # series-major chunk [voxel][k][resample]: the sort reads every series as one contiguous run (the
+                # resample-major cube read in place with a stride of the chunk size cost 23-41 ms per chunk against 17)
+                cube = self._empty(v1 - v0, K, R)
+                check(lib.plsb200_salience_series_f64(X.data_ptr() + 8 * v0, self.N, v1 - v0, self.ldx, self._p(E), K,
+                                                      self._p(idx), R, self._p(cube), self._stream()), "salience_series_f64")
+                check(lib.plsb200_percentile_f64(self._p(cube), R, (v1 - v0) * K, 1, R, float(conf[0]), float(conf[1]),
+                                                 lo.data_ptr() + 8 * v0 * K, hi.data_ptr() + 8 * v0 * K, self._p(ws), nb,
+                                                 self._stream()), "percentile_f64")
+                del cube
         return lo, hi
 
     def salience(self, E, idx, M=None):

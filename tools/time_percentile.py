@@ -37,3 +37,16 @@ total_ms, (LO, HI) = timed(lambda: eng.salience_percentiles(Ed, idd, (0.025, 0.9
 print(json.dumps({"p": p, "R": R, "K": K, "chunk_voxels": vc, "salience_chunk_ms": cube_ms, "sort_chunk_ms": sort_ms,
                   "series_per_s": vc * K / sort_ms * 1e3, "salience_tflops": 2.0 * N * K * R * vc / cube_ms * 1e-9,
                   "whole_ms": total_ms, "check": float((HI - LO).mean())}))
+
+# the same sort on a SERIES-major copy of the chunk (stride 1 between samples): what the strided in-place reads cost
+from plspy_b200._lib import lib, check
+cube = eng.salience(Ed, idd, M=eng.X[:, :vc])
+ct = cube.permute(1, 2, 0).contiguous()
+M = vc * K
+lo2 = torch.empty(M, dtype=torch.float64, device="cuda"); hi2 = torch.empty_like(lo2)
+ws = eng._ws(16)
+ms_t, _ = timed(lambda: check(lib.plsb200_percentile_f64(ct.data_ptr(), R, M, 1, R, 0.025, 0.975, lo2.data_ptr(), hi2.data_ptr(),
+                                                          ws.data_ptr(), 16, eng._stream()), "pc"), reps=3)
+ms_s, (lo1, hi1) = timed(lambda: eng.percentile_interval(cube, (0.025, 0.975)), reps=3)
+print(json.dumps({"sort_chunk_ms_strided": ms_s, "sort_chunk_ms_series_major": ms_t,
+                  "equal": bool(torch.equal(lo1.reshape(-1), lo2) and torch.equal(hi1.reshape(-1), hi2))}))
