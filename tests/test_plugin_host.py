@@ -70,3 +70,25 @@ def test_uninstall_restores_the_reference(ref_plspy):
     plspy_b200.install(ref_plspy)                                # idempotent: the saved originals are not overwritten
     plspy_b200.uninstall()
     assert {c.__module__ for c in ref_bp.ResampleTest._subclasses.values()} == {"plspy.core.bootstrap_permutation"}
+
+
+@pytest.mark.parametrize("groups,C,p,nb,offset", [((5, 7), 2, 301, 3, 100.0), ((20, 20), 3, 60000, 4, 0.0), ((4,), 1, 50, 1, 0.0)])
+def test_host_compute_corr_matches_the_reference_function(groups, C, p, nb, offset):
+    """plspy_b200.class_functions._compute_corr (scale after the product, blocks on threads for a wide X) against the
+    unmodified reference's element-wise z-score version (plspy/core/class_functions.py:185-247), incl. a constant column"""
+    import warnings
+    from plspy_b200 import class_functions as cf
+    ref_cf = baseline.import_reference().core.class_functions
+    rs = np.random.RandomState(p)
+    co = np.array([[n] * C for n in groups])
+    N = int(co.sum())
+    X = rs.standard_normal((N, p)) + offset
+    Y = rs.standard_normal((N, nb))
+    X[:, 5] = 3.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ref_cf._compute_corr(X, Y, co)
+    got = cf._compute_corr(X, Y, co)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-15 * max(1.0, abs(offset)))
+    assert np.all(got[:, 5] == 0.0)
