@@ -67,11 +67,24 @@ def shard(n, rank=None, size=None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _staged(t):
+    """gloo implements only some collectives for CUDA tensors: device tensors are staged through the host there (two
+    processes sharing ONE GPU over gloo is how the sharded code path is tested on a single-GPU box; NCCL refuses two
+    ranks on one device)."""
+    import torch.distributed as dist
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
 def allreduce_sum_(t):
     """In-place sum over ranks (no-op for a single process). Integer counters reduce exactly."""
     import torch.distributed as dist
     if world()[1] > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if _staged(t):
+            c = t.cpu()
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            t.copy_(c)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 
@@ -103,8 +116,13 @@ def gather_rows(local, n_total, lo):
     if local.shape[0] != mx:
         buf = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
         buf[:local.shape[0]] = local
-    out = torch.empty((size * mx,) + tail, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, buf.contiguous())
+    if _staged(local):
+        out_h = torch.empty((size * mx,) + tail, dtype=local.dtype)
+        dist.all_gather_into_tensor(out_h, buf.contiguous().cpu())
+        out = out_h.to(local.device)
+    else:
+        out = torch.empty((size * mx,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, buf.contiguous())
     if all(hi - l == mx for l, hi in spans):
         return out
     return torch.cat([out[r * mx:r * mx + (hi - l)] for r, (l, hi) in enumerate(spans)], dim=0)
