@@ -25,7 +25,7 @@ def call():
     return time.perf_counter() - t0
 
 
-for pf in ("1", "0"):
+for pf in (_os.environ.get("PF_MODES", "1,0").split(",")):
     _os.environ["PLSB200_PREFETCH"] = pf
     ts = [call() for _ in range(4)]
     pr = cProfile.Profile(); pr.enable(); call(); pr.disable()
