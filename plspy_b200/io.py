@@ -100,6 +100,14 @@ def create_threshold_mask_from_matrices(matrices, threshold=0.15):
     return np.asarray(mask)
 
 
+def create_binary_mask_from_matrices(matrices):
+    """plspy/io/io.py:316-350 -- True where no subject has a zero at any time point (`logical_and` over all volumes of
+    all subjects, zeros counting as False)."""
+    mats = np.array(matrices)
+    mats_concat = mats.reshape((-1,) + mats.shape[2:])
+    return np.logical_and.reduce(mats_concat, where=(mats_concat != 0), axis=0)
+
+
 def apply_mask_matrices(matrices, mask):
     """plspy/io/io.py:427-460 -- every matrix flattened to its masked elements (time-major)."""
     return [m[np.broadcast_to(mask, m.shape)] for m in matrices]

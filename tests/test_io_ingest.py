@@ -96,6 +96,7 @@ def test_ingest_steps_match_the_reference_functions():
     a_ref, a = ref.apply_mask_matrices(mats, mask), gio.apply_mask_matrices(mats, mask)
     assert all(np.array_equal(x, y) for x, y in zip(a_ref, a))
     assert np.array_equal(ref.create_and_apply_mask_list(mats), gio.create_and_apply_mask_list(mats))
+    assert np.array_equal(ref.create_binary_mask_from_matrices(mats), gio.create_binary_mask_from_matrices(mats))
     onsets = np.array([[0, 3], [1, 4]])                                   # conditions x onsets
     s_ref = ref.extract_onset_slices_single_subject(mats[0], onsets, 1, 2.0)
     s = gio.extract_onset_slices_single_subject(mats[0], onsets, 1, 2.0)
